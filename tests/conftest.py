@@ -1,0 +1,45 @@
+import gzip
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def golden_names(kind=None):
+    names = sorted(f[:-6] for f in os.listdir(GOLDEN_DIR) if f.endswith(".pt.gz"))
+    if kind is not None:
+        names = [n for n in names if n.startswith(kind)]
+    return names
+
+
+def load_golden(name):
+    with gzip.open(os.path.join(GOLDEN_DIR, name + ".pt.gz"), "rb") as f:
+        return torch.load(f, map_location="cpu", weights_only=False)
+
+
+def rel_err(a, b):
+    """Norm-wise relative error max|a-b| / max|b| (the parity measure used throughout)."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    denom = b.abs().max().item()
+    if denom == 0.0:
+        return (a - b).abs().max().item()
+    return (a - b).abs().max().item() / denom
+
+
+@pytest.fixture(scope="session")
+def cuda_device():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
