@@ -1,0 +1,135 @@
+/*
+ * mrla_b200.h — C ABI of libmrla_b200.so (hand-written sm_100a kernels for the MRLA block tail).
+ *
+ * The reference (joyfang1106/MRLA) is pure Python/PyTorch and has no FFI of its own; the
+ * "interface each entry point replaces" is therefore the sequence of ATen calls issued by the
+ * reference modules.  Paths below are relative to /root/reference.
+ *
+ *   mrla_light_forward / mrla_light_backward
+ *       replace  resnet/models/modules/mrla_light_module.py:52-74   (mrla_light_layer.forward)
+ *                resnet/models/resnet_mrla_light.py:40-43            (mrla_module.forward, lambda recurrence)
+ *                resnet/models/resnet_mrla_light.py:116              (bn_mrla + drop_path + residual)
+ *                resnet/models/utils/drop.py:17-23                   (DropPath, consumed as a [B] scale)
+ *                mmdetection/mmdet/models/backbones/resnet_mrlal.py:116 (eval-BN variant, bn_mode=2)
+ *                deit/deit_mrla_light.py:157-180,204-206             (token layout, GELU on V, act=1, bn_mode=0)
+ *       and the autograd graph PyTorch builds for them.
+ *
+ *   mrla_base_forward / mrla_base_backward
+ *       replace  resnet/models/modules/mrla_base_module.py:54-89    (mrla_base_layer.forward)
+ *                resnet/models/resnet_mrla_base.py:124-127           (bn_mrla + relu + drop_path + residual)
+ *                deit/deit_mrla_base.py:166-201,224-243              (token layout, bn_mode=0)
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller; the library never allocates,
+ *     frees or retains memory, never synchronises the host and only enqueues work on `stream`
+ *     (a cudaStream_t passed as void*), so calls are CUDA-graph capturable and re-entrant.
+ *   - return value: 0 = success; negative = argument / shape / alignment / unsupported-config
+ *     error detected before any launch (see MRLA_ERR_*); positive = cudaError_t from a launch.
+ *   - activations x,o,y,dy,dx,dout use `dtype` (fp32 / bf16 / fp16) in `layout`; all parameters,
+ *     statistics, [B,C] side tensors and gradients of parameters are fp32.
+ *   - NCHW: element (b,c,h,w) lives at  b*bs + (c*H + h)*W + w ;
+ *     NHWC: element (b,c,h,w) lives at  b*bs + (h*W + w)*C + c   (channels_last / token-major).
+ *     `bs_*` are per-tensor batch strides in elements (lets DeiT pass the [B,197,C] token
+ *     buffer offset by one token, and MRLA-base pass slots of a [B,T,C,H,W] cache).
+ */
+#ifndef MRLA_B200_H_
+#define MRLA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRLA_ABI_VERSION 1
+
+enum { MRLA_F32 = 0, MRLA_BF16 = 1, MRLA_F16 = 2 };
+enum { MRLA_NCHW = 0, MRLA_NHWC = 1 };
+enum { MRLA_ACT_NONE = 0, MRLA_ACT_GELU = 1 };
+enum { MRLA_BN_NONE = 0, MRLA_BN_TRAIN = 1, MRLA_BN_EVAL = 2 };
+
+enum {
+  MRLA_OK = 0,
+  MRLA_ERR_NULL = -1,        /* a required pointer is NULL                          */
+  MRLA_ERR_SHAPE = -2,       /* B,C,H,W,d,k out of the supported range             */
+  MRLA_ERR_ALIGN = -3,       /* pointer / stride not aligned for the vector width  */
+  MRLA_ERR_UNSUPPORTED = -4, /* dtype / layout / flag combination not implemented  */
+  MRLA_ERR_WORKSPACE = -5    /* scratch buffer too small                           */
+};
+
+/* One MRLA-light block tail (forward and backward share the struct; unused fields may be NULL). */
+typedef struct MrlaLightArgs {
+  /* ---- problem ---- */
+  int32_t B, C, H, W;
+  int32_t dim_perhead;  /* d; heads g = C/d (mrla_light_module.py:32-38)                       */
+  int32_t k_size;       /* ECA kernel size (mrla_light_module.py:40-43), odd                   */
+  int32_t dtype;        /* MRLA_F32 / MRLA_BF16 / MRLA_F16                                       */
+  int32_t layout;       /* MRLA_NCHW / MRLA_NHWC                                                */
+  int32_t act;          /* MRLA_ACT_GELU: V = gelu(dwconv(x)) (deit_mrla_light.py:166-167)      */
+  int32_t bn_mode;      /* MRLA_BN_*                                                           */
+  int32_t residual;     /* 1: y = x + branch (resnet_mrla_light.py:116); 0: y = branch          */
+  int32_t update_running; /* 1: BN train mode also updates running_mean/var in place            */
+  float eps, momentum;  /* BatchNorm2d eps / momentum                                          */
+  int64_t bs_x, bs_o, bs_y, bs_dy, bs_dx, bs_do; /* batch strides (elements)                    */
+  /* ---- forward tensors ---- */
+  const void* x;            /* xt  [B,C,H,W]                                                    */
+  const void* o;            /* ot_1 [B,C,H,W] or NULL (layer only: no lambda term)              */
+  void* y;                  /* out [B,C,H,W]                                                    */
+  const float* wq;          /* [k]                                                              */
+  const float* wk;          /* [k]                                                              */
+  const float* wv;          /* [C,3,3]                                                          */
+  const float* lam;         /* [C] or NULL                                                      */
+  const float* gamma;       /* [C] BN weight (NULL when bn_mode == NONE)                        */
+  const float* beta;        /* [C] BN bias                                                      */
+  float* running_mean;      /* [C] (read in eval, updated in train when update_running)         */
+  float* running_var;       /* [C]                                                              */
+  const float* drop_scale;  /* [B] DropPath scale m_b (0 or 1/keep) or NULL                     */
+  /* ---- saved for backward (written by forward, read by backward), fp32 ---- */
+  float* mom;   /* [6,B,C]: sum_hw of x, V, V^2, V*o, o, o^2                                     */
+  float* gate;  /* [B,C/d] sigmoid gate                                                         */
+  float* mean;  /* [C] BN batch (or running) mean actually used                                 */
+  float* rstd;  /* [C] 1/sqrt(var+eps)                                                          */
+  float* coef;  /* [3,B,C] forward per-(b,c) coefficients (scratch, not needed by backward)     */
+  /* ---- backward tensors ---- */
+  const void* dy;  /* [B,C,H,W] */
+  void* dx;        /* [B,C,H,W] */
+  void* dout;      /* [B,C,H,W] grad of o, or NULL */
+  float* dwq;      /* [k]  (overwritten) */
+  float* dwk;      /* [k]    */
+  float* dwv;      /* [C,9]  */
+  float* dlam;     /* [C] or NULL */
+  float* dgamma;   /* [C] or NULL */
+  float* dbeta;    /* [C] or NULL */
+  /* ---- backward scratch, fp32 ---- */
+  float* gmom;     /* [3,B,C] */
+  float* bcoef;    /* [7,B,C] */
+  float* scratch;  /* partial reductions; size from mrla_light_bwd_scratch_bytes() */
+  size_t scratch_bytes;
+} MrlaLightArgs;
+
+int mrla_abi_version(void);
+
+/* last CUDA error string / library build info (static storage). */
+const char* mrla_build_info(void);
+
+/* sizeof(MrlaLightArgs) as compiled — lets a foreign-language binding verify its struct mirror. */
+size_t mrla_sizeof_light_args(void);
+
+/* bytes of `scratch` mrla_light_backward needs for this problem. */
+size_t mrla_light_bwd_scratch_bytes(const MrlaLightArgs* a);
+
+/* y = residual*x + m_b*( BN( gate(x)*act(dwconv3x3(x)) + lambda*o ) ), plus saved statistics. */
+int mrla_light_forward(const MrlaLightArgs* a, void* stream);
+
+/* dx, dout and all parameter gradients of the same expression. */
+int mrla_light_backward(const MrlaLightArgs* a, void* stream);
+
+/* Number of kernel launches the last forward / backward call on this thread enqueued
+ * (bench.py reports it as gpu_launches). */
+int mrla_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRLA_B200_H_ */

@@ -1,0 +1,94 @@
+"""ctypes binding of libmrla_b200.so (C ABI declared in include/mrla_b200.h).
+
+There is no CPU fallback and no alternative backend: if the shared library is missing or a
+tensor is not on a CUDA device the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmrla_b200.so")
+ABI_VERSION = 1
+
+F32, BF16, F16 = 0, 1, 2
+NCHW, NHWC = 0, 1
+ACT_NONE, ACT_GELU = 0, 1
+BN_NONE, BN_TRAIN, BN_EVAL = 0, 1, 2
+
+ERRORS = {
+    -1: "MRLA_ERR_NULL (a required pointer is NULL)",
+    -2: "MRLA_ERR_SHAPE (B,C,H,W,d,k out of the supported range)",
+    -3: "MRLA_ERR_ALIGN (pointer / stride / channel count not aligned for the vector width)",
+    -4: "MRLA_ERR_UNSUPPORTED (dtype / layout / flag combination not implemented)",
+    -5: "MRLA_ERR_WORKSPACE (scratch buffer too small)",
+}
+
+_vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+
+
+class MrlaLightArgs(ctypes.Structure):
+    """Mirror of `struct MrlaLightArgs` (include/mrla_b200.h) — field order must match."""
+    _fields_ = (
+        [(n, _i32) for n in ("B", "C", "H", "W", "dim_perhead", "k_size", "dtype", "layout", "act", "bn_mode",
+                             "residual", "update_running")]
+        + [("eps", _f32), ("momentum", _f32)]
+        + [(n, _i64) for n in ("bs_x", "bs_o", "bs_y", "bs_dy", "bs_dx", "bs_do")]
+        + [(n, _vp) for n in ("x", "o", "y", "wq", "wk", "wv", "lam", "gamma", "beta", "running_mean", "running_var",
+                              "drop_scale", "mom", "gate", "mean", "rstd", "coef", "dy", "dx", "dout", "dwq", "dwk",
+                              "dwv", "dlam", "dgamma", "dbeta", "gmom", "bcoef", "scratch")]
+        + [("scratch_bytes", ctypes.c_size_t)]
+    )
+
+
+_lib = None
+_lock = threading.Lock()
+
+EXPORTS = (
+    "mrla_abi_version", "mrla_build_info", "mrla_last_launch_count", "mrla_sizeof_light_args",
+    "mrla_light_bwd_scratch_bytes", "mrla_light_forward", "mrla_light_backward",
+)
+
+
+def lib() -> ctypes.CDLL:
+    """Load libmrla_b200.so once; fail loudly if it is absent or has the wrong ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: the CUDA extension has not been built "
+                "(run `python -c 'import __graft_entry__ as g; g.build()'` or `make -C mrla_b200/csrc -j`). "
+                "mrla_b200 has no CPU or PyTorch fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        L.mrla_abi_version.restype = ctypes.c_int
+        if L.mrla_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"libmrla_b200.so ABI {L.mrla_abi_version()} != expected {ABI_VERSION}; rebuild")
+        L.mrla_build_info.restype = ctypes.c_char_p
+        L.mrla_last_launch_count.restype = ctypes.c_int
+        L.mrla_sizeof_light_args.restype = ctypes.c_size_t
+        if L.mrla_sizeof_light_args() != ctypes.sizeof(MrlaLightArgs):
+            raise RuntimeError("MrlaLightArgs layout mismatch between _lib.py and include/mrla_b200.h")
+        for name, st in (("light", MrlaLightArgs),):
+            f = getattr(L, f"mrla_{name}_bwd_scratch_bytes")
+            f.restype = ctypes.c_size_t
+            f.argtypes = [ctypes.POINTER(st)]
+            for d in ("forward", "backward"):
+                f = getattr(L, f"mrla_{name}_{d}")
+                f.restype = ctypes.c_int
+                f.argtypes = [ctypes.POINTER(st), ctypes.c_void_p]
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc == 0:
+        return
+    if rc < 0:
+        raise RuntimeError(f"{what}: {ERRORS.get(rc, rc)}")
+    raise RuntimeError(f"{what}: CUDA error {rc} at launch")

@@ -1,0 +1,91 @@
+// extern "C" entry points of libmrla_b200.so (see include/mrla_b200.h).
+#include "light_launch.cuh"
+
+namespace mrla {
+thread_local int g_launch_count = 0;
+extern template int light_forward_t<float>(const MrlaLightArgs&, cudaStream_t);
+extern template int light_backward_t<float>(const MrlaLightArgs&, cudaStream_t);
+extern template int light_forward_t<__nv_bfloat16>(const MrlaLightArgs&, cudaStream_t);
+extern template int light_backward_t<__nv_bfloat16>(const MrlaLightArgs&, cudaStream_t);
+extern template int light_forward_t<__half>(const MrlaLightArgs&, cudaStream_t);
+extern template int light_backward_t<__half>(const MrlaLightArgs&, cudaStream_t);
+
+static size_t esize(int dtype) { return dtype == MRLA_F32 ? 4 : 2; }
+
+static int check_common(const MrlaLightArgs* a, bool bwd) {
+  if (a == nullptr) return MRLA_ERR_NULL;
+  if (a->B < 1 || a->C < 1 || a->H < 1 || a->W < 1) return MRLA_ERR_SHAPE;
+  if (a->dim_perhead < 1 || a->C % a->dim_perhead) return MRLA_ERR_SHAPE;
+  if (a->k_size < 1 || a->k_size > 15 || a->k_size % 2 == 0) return MRLA_ERR_SHAPE;
+  if (a->dtype < MRLA_F32 || a->dtype > MRLA_F16) return MRLA_ERR_UNSUPPORTED;
+  if (a->layout != MRLA_NCHW && a->layout != MRLA_NHWC) return MRLA_ERR_UNSUPPORTED;
+  if (a->act != MRLA_ACT_NONE && a->act != MRLA_ACT_GELU) return MRLA_ERR_UNSUPPORTED;
+  if (a->bn_mode < MRLA_BN_NONE || a->bn_mode > MRLA_BN_EVAL) return MRLA_ERR_UNSUPPORTED;
+  if (!a->x || !a->wq || !a->wk || !a->wv || !a->mom || !a->gate || !a->mean || !a->rstd) return MRLA_ERR_NULL;
+  if (a->o && !a->lam) return MRLA_ERR_NULL;
+  if (a->bn_mode != MRLA_BN_NONE && (!a->gamma || (!bwd && !a->beta))) return MRLA_ERR_NULL;
+  if (!bwd && a->bn_mode == MRLA_BN_EVAL && (!a->running_mean || !a->running_var)) return MRLA_ERR_NULL;
+  if (a->layout == MRLA_NHWC) {
+    // 4-channel vectors: base pointers and batch strides must keep them aligned
+    const size_t al = 4 * esize(a->dtype);
+    if (a->C % 4) return MRLA_ERR_ALIGN;
+    const void* ptrs[] = {a->x, a->o, a->y, a->dy, a->dx, a->dout};
+    for (const void* p : ptrs)
+      if (p && ((uintptr_t)p % al)) return MRLA_ERR_ALIGN;
+    const int64_t bss[] = {a->bs_x, a->bs_o, a->bs_y, a->bs_dy, a->bs_dx, a->bs_do};
+    for (int64_t s : bss)
+      if (s % 4) return MRLA_ERR_ALIGN;
+  }
+  return MRLA_OK;
+}
+}  // namespace mrla
+
+using namespace mrla;
+
+extern "C" {
+
+int mrla_abi_version(void) { return MRLA_ABI_VERSION; }
+
+const char* mrla_build_info(void) {
+#define MRLA_STR2(x) #x
+#define MRLA_STR(x) MRLA_STR2(x)
+  return "mrla_b200 sm_100a nvcc " MRLA_STR(__CUDACC_VER_MAJOR__) "." MRLA_STR(__CUDACC_VER_MINOR__) " built " __DATE__ " " __TIME__;
+}
+
+int mrla_last_launch_count(void) { return g_launch_count; }
+
+size_t mrla_sizeof_light_args(void) { return sizeof(MrlaLightArgs); }
+
+size_t mrla_light_bwd_scratch_bytes(const MrlaLightArgs* a) {
+  if (a == nullptr) return 0;
+  return light_bwd_scratch_floats(*a) * sizeof(float);
+}
+
+int mrla_light_forward(const MrlaLightArgs* a, void* stream) {
+  g_launch_count = 0;
+  int rc = check_common(a, false);
+  if (rc) return rc;
+  if (!a->y || !a->coef) return MRLA_ERR_NULL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (a->dtype) {
+    case MRLA_F32: return light_forward_t<float>(*a, st);
+    case MRLA_BF16: return light_forward_t<__nv_bfloat16>(*a, st);
+    default: return light_forward_t<__half>(*a, st);
+  }
+}
+
+int mrla_light_backward(const MrlaLightArgs* a, void* stream) {
+  g_launch_count = 0;
+  int rc = check_common(a, true);
+  if (rc) return rc;
+  if (!a->dy || !a->dx || !a->gmom || !a->bcoef || !a->scratch) return MRLA_ERR_NULL;
+  if (a->o && !a->dout) return MRLA_ERR_NULL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (a->dtype) {
+    case MRLA_F32: return light_backward_t<float>(*a, st);
+    case MRLA_BF16: return light_backward_t<__nv_bfloat16>(*a, st);
+    default: return light_backward_t<__half>(*a, st);
+  }
+}
+
+}  // extern "C"
