@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — resnet50_mrlal training throughput on N B200s (BASELINE.json configs[1]) + MRLA-tail roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # product arm (CUDA kernels via the C ABI)
+    python bench.py --impl reference [--steps K] [--warmup W]       # reference arm: the reference's CPU path
+
+One "step" = forward + loss + backward + SGD update of `resnet50_mrlal` on one synthetic batch
+(256 x 3 x 224 x 224 per GPU, bf16 autocast, channels_last, random-init weights, drop_path 0.2 as
+resnet/train.py:67 of the reference).  Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+import torch.nn as nn  # noqa: E402
+
+METRIC = "resnet50_mrlal_train_images_per_sec"
+STAGE_BLOCKS = {(256, 56): 3, (512, 28): 4, (1024, 14): 6, (2048, 7): 3}
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy burst)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.f.read().splitlines():
+            parts = [s.strip() for s in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        if sm:
+            # "under load" = samples with power in the upper half of the observed range
+            thr = (max(pw) + min(pw)) / 2 if pw else 0
+            load = [s for s, p_ in zip(sm, pw) if p_ >= thr] or sm
+            out.update(sm_mhz=statistics.median(load), sm_max_mhz=max(mx), reasons=sorted(reasons),
+                       power_w_max=max(pw), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_run(steps: int, warmup: int, batch: int = 32):
+    """The reference's CPU path (oracle port of resnet50_mrlal; /root/reference is absent on the GPU box):
+    fwd+bwd of BASELINE.json configs[0] (batch 32 x 3 x 224 x 224 fp32) on all host cores."""
+    from oracle.resnet_oracle import resnet50_mrlal_oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = resnet50_mrlal_oracle(drop_path=0.0).train()
+    x = torch.randn(batch, 3, 224, 224)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        model.zero_grad(set_to_none=True)
+        y = model(x)
+        y.sum().backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    cpu_name = ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                cpu_name = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return dict(img_per_s=batch * len(times) / total, ms_per_step=1e3 * total / len(times), cores=cores,
+                threads=torch.get_num_threads(), cpu=cpu_name, batch=batch)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 10))
+    warmup = max(1, min(args.warmup, 2))
+    r = cpu_reference_run(steps, warmup)
+    sample = (f"oracle port of reference resnet50_mrlal (resnet/models/resnet_mrla_light.py), fwd+bwd, batch {r['batch']}"
+              f" x3x224x224 fp32 (BASELINE configs[0]), {steps} timed + {warmup} warm-up iterations, {r['cpu']}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(r["img_per_s"], 3), "unit": "img/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(r["ms_per_step"], 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "resnet50_mrlal train step (fwd+bwd), 224x224 synthetic, CPU sample batch 32 fp32",
+                   "model": "resnet50_mrlal", "device": "host CPU"},
+        "cpu_baseline": {"value": round(r["img_per_s"], 3), "unit": "img/s", "cores": r["threads"], "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": round(r["img_per_s"], 3), "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ product arm
+def summarize_prof(records, peak):
+    """records: (tag, (B,C,H,W,dtype,layout), ev0, ev1) from mrla_b200.ops._Prof -> per-shape fwd/bwd ms."""
+    agg = {}
+    for tag, key, e0, e1 in records:
+        B, C, H, W, dt, lay = key
+        agg.setdefault((C, H, B, dt), {"light_fwd": [], "light_bwd": []})[tag].append(e0.elapsed_time(e1))
+    out = {}
+    tot_bytes = tot_ms = 0.0
+    for (C, H, B, dt), d in agg.items():
+        if not d["light_fwd"] or not d["light_bwd"]:
+            continue
+        f = sum(d["light_fwd"]) / len(d["light_fwd"])
+        b = sum(d["light_bwd"]) / len(d["light_bwd"])
+        es = torch.empty((), dtype=dt).element_size()
+        nbytes = 8.0 * B * C * H * H * es
+        out[(C, H)] = dict(fwd_ms=f, bwd_ms=b, bytes=nbytes, gbs=nbytes / (f + b) / 1e6, calls=len(d["light_fwd"]))
+        n = STAGE_BLOCKS.get((C, H), 0)
+        tot_bytes += n * nbytes
+        tot_ms += n * (f + b)
+    return out, tot_bytes, tot_ms
+
+
+def run_product_arm(args):
+    from mrla_b200 import ops
+    from mrla_b200.resnet_mrla_light import resnet50_mrlal
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    torch.manual_seed(0)
+    torch.backends.cudnn.benchmark = True
+    model = resnet50_mrlal(drop_path=args.drop_path).to(dev).to(memory_format=torch.channels_last).train()
+    opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)  # reference train.py:199
+    net = model
+    if world > 1:
+        net = nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)
+    crit = nn.CrossEntropyLoss().to(dev)
+    gen = torch.Generator(device="cpu").manual_seed(1 + rank)
+    # synthetic ImageNet-shaped batch: device-resident for `value`, pinned host copies for `e2e`
+    host_img = [torch.randn(B, 3, 224, 224, generator=gen).pin_memory() for _ in range(2)]
+    host_lbl = [torch.randint(0, 1000, (B,), generator=gen).pin_memory() for _ in range(2)]
+    dev_img = host_img[0].to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dev_lbl = host_lbl[0].to(dev)
+
+    def step(img, lbl):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = net(img)
+        loss = crit(out.float(), lbl)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    W, K = args.warmup, args.steps
+    for _ in range(W):
+        step(dev_img, dev_lbl)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM ----
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ops._Prof.enabled = (rank == 0)
+    ops._Prof.records = []
+    l0 = ops.launch_counter["fwd"] + ops.launch_counter["bwd"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        step(dev_img, dev_lbl)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = ops.launch_counter["fwd"] + ops.launch_counter["bwd"] - l0
+    ops._Prof.enabled = False
+    prof_records = ops._Prof.records
+    clocks = sampler.stop() if sampler else None
+
+    # ---- timed region 2 (e2e): pinned host batch -> H2D every step, loss read back every step ----
+    copy_stream = torch.cuda.Stream()
+    slots = [None, None]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            img = host_img[i % 2].to(dev, non_blocking=True)
+            lbl = host_lbl[i % 2].to(dev, non_blocking=True)
+            img = img.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        slots[i % 2] = (img, lbl, ev)
+
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    prefetch(0)
+    last_loss = 0.0
+    for i in range(K):
+        img, lbl, ev = slots[i % 2]
+        torch.cuda.current_stream().wait_event(ev)
+        img.record_stream(torch.cuda.current_stream())
+        if i + 1 < K:
+            prefetch(i + 1)
+        loss = step(img, lbl)
+        last_loss = float(loss.item())  # D2H read of the step's result
+    s1.record()
+    barrier()
+    ms_e2e = max_over_ranks(s0.elapsed_time(s1))
+    h2d = host_img[0].numel() * 4 + host_lbl[0].numel() * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_kind = peaks()
+    per_shape, tot_bytes, tot_ms = summarize_prof(prof_records, peak)
+    roof = None
+    if (256, 56) in per_shape:
+        d = per_shape[(256, 56)]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("stage1_tail_fwd_bwd_dram_bytes")
+            except Exception:
+                traffic = None
+        roof = {"bound": "hbm", "achieved": round(d["gbs"], 1), "peak": peak, "unit": "GB/s",
+                "frac": round(d["gbs"] / peak, 4), "traffic": traffic,
+                "kernel": "MRLA-light tail fwd+bwd kernel group, stage-1 shape (B,256,56,56) bf16 NHWC "
+                          "(sweep1+mid+sweep2 / sweepA+mid+sweepB+finish), algorithmic bytes 8*N*2",
+                "peak_kind": peak_kind,
+                "launch_ms": {"fwd": round(d["fwd_ms"], 4), "bwd": round(d["bwd_ms"], 4)},
+                "all_16_tails": {"ms_per_step": round(tot_ms, 3), "alg_GB_per_step": round(tot_bytes / 1e9, 3),
+                                 "achieved": round(tot_bytes / tot_ms / 1e6, 1) if tot_ms else None,
+                                 "frac": round(tot_bytes / tot_ms / 1e6 / peak, 4) if tot_ms else None},
+                "per_stage": {f"{c}x{h}x{h}": {"fwd_ms": round(v["fwd_ms"], 4), "bwd_ms": round(v["bwd_ms"], 4),
+                                               "GBps": round(v["gbs"], 1)} for (c, h), v in per_shape.items()}}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(steps=2, warmup=1)
+        cpu = {"value": round(r["img_per_s"], 3), "unit": "img/s", "cores": r["threads"], "kind": "port",
+               "sample": f"oracle port of reference resnet50_mrlal fwd+bwd, batch {r['batch']} x3x224x224 fp32 "
+                         f"(BASELINE configs[0]), 2 timed + 1 warm-up iterations, {r['ms_per_step']:.0f} ms/iter, {r['cpu']}"}
+    line = {
+        "metric": METRIC, "value": round(world * B * K / (ms / 1e3), 2), "unit": "img/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "resnet50_mrlal training step (fwd+loss+bwd+SGD), BASELINE configs[1]",
+                   "model": "resnet50_mrlal", "per_gpu_batch": B, "global_batch": B * world, "image": "3x224x224",
+                   "precision": "bf16 autocast, fp32 master weights", "memory_format": "channels_last",
+                   "drop_path": args.drop_path, "parallelism": f"dp{world}" + (" (DDP/NCCL)" if world > 1 else ""),
+                   "l2": "inputs exceed L2 (per-step activations >> 126 MB); no explicit flush"},
+        "clocks": clocks,
+        "e2e": {"value": round(world * B * K / (ms_e2e / 1e3), 2), "unit": "img/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / K, 3), "last_loss": round(last_loss, 4)},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--drop-path", type=float, default=0.2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world != args.gpus and world == 1 and args.gpus > 1:
+            # convenience: re-launch under torchrun when invoked directly with --gpus N
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+            raise SystemExit(subprocess.call(cmd))
+        run_product_arm(args)
+
+
+if __name__ == "__main__":
+    main()
