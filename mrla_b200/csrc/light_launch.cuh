@@ -3,6 +3,7 @@
 #include "../../include/mrla_b200.h"
 #include "light_mid.cuh"
 #include "light_sweeps.cuh"
+#include "light_nhwc_tma.cuh"
 
 namespace mrla {
 
@@ -69,6 +70,163 @@ inline MidShape mid_shape(const MrlaLightArgs& a, bool full) {
   return m;
 }
 
+// ------------------------------------------------------------------------------------ v2 (TMA) planning
+struct TmaPlan {
+  int CB, NQ, G, S, ncb, items, cons_threads, grid;
+  uint32_t x_bytes, o_bytes, stage_bytes;
+  size_t smem;
+};
+
+// ntiles = number of [CB,W,G] tiles per stage besides the x tile (o and/or dy); nacc = float2 accumulators/thread
+inline bool make_tma_plan(const MrlaLightArgs& a, int ntiles, int nacc, TmaPlan* p) {
+  if (a.layout != MRLA_NHWC || a.C % 8 || a.W > 56) return false;
+  const int es = a.dtype == MRLA_F32 ? 4 : 2;
+  const int NQ = (a.W + kCols - 1) / kCols;
+  int CB = 0;
+  for (int cb : {256, 128, 64})
+    if (NQ * cb / 2 <= 448 && (a.C % cb == 0 || (cb == 64 && a.C > 64))) { CB = cb; break; }
+  if (CB == 0) {
+    if (NQ * 32 <= 448) CB = 64; else return false;
+  }
+  if (a.act == MRLA_ACT_GELU && CB == 256) CB = 128;
+  const uint32_t xrow = (uint32_t)(a.W + 2) * CB * es, orow = (uint32_t)a.W * CB * es;
+  int G;
+  if ((size_t)a.H * xrow <= 40 * 1024) G = a.H;
+  else { G = (int)(16384 / xrow); if (G < 1) G = 1; if (G > a.H) G = a.H; }
+  p->CB = CB; p->NQ = NQ; p->G = G;
+  p->x_bytes = (uint32_t)G * xrow;
+  p->o_bytes = (uint32_t)G * orow;
+  p->stage_bytes = p->x_bytes + (uint32_t)ntiles * p->o_bytes;
+  const size_t red = (size_t)NQ * nacc * (CB / 2) * sizeof(float2);
+  const size_t budget = 200 * 1024;
+  int S = (int)((budget - red) / p->stage_bytes);
+  if (S > 8) S = 8;
+  if (S < 2) return false;
+  p->S = S;
+  p->ncb = (a.C + CB - 1) / CB;
+  p->items = a.B * p->ncb;
+  p->cons_threads = NQ * (CB / 2);
+  p->grid = p->items < kNumSMs ? p->items : kNumSMs;
+  p->smem = 256 + (size_t)S * p->stage_bytes + red;
+  return true;
+}
+
+inline bool tma_ptr_ok(const void* ptr, int64_t bs, int es) {
+  return ptr != nullptr && ((uintptr_t)ptr % 16 == 0) && ((bs * es) % 16 == 0);
+}
+
+template <typename T, int ACT, int MODE>
+int launch_tma_sweep(const MrlaLightArgs& a, cudaStream_t st, const TmaPlan& p, const void* xptr, int64_t bs_x,
+                     const void* optr, int64_t bs_o, const void* dyptr, int64_t bs_dy, float* mom) {
+  CUtensorMap tx, to, tdy;
+  if (make_nhwc_tmap(&tx, xptr, a.dtype, a.B, a.C, a.H, a.W, bs_x, p.CB, a.W + 2, p.G)) return MRLA_ERR_UNSUPPORTED;
+  if (make_nhwc_tmap(&to, optr, a.dtype, a.B, a.C, a.H, a.W, bs_o, p.CB, a.W, p.G)) return MRLA_ERR_UNSUPPORTED;
+  tdy = to;
+  if (MODE == 2 && make_nhwc_tmap(&tdy, dyptr, a.dtype, a.B, a.C, a.H, a.W, bs_dy, p.CB, a.W, p.G))
+    return MRLA_ERR_UNSUPPORTED;
+  TmaSweepParams P;
+  P.B = a.B; P.C = a.C; P.H = a.H; P.W = a.W;
+  P.G = p.G; P.S = p.S; P.NQ = p.NQ; P.ncb = p.ncb; P.items = p.items; P.cons_threads = p.cons_threads;
+  P.x_bytes = p.x_bytes; P.o_bytes = p.o_bytes; P.stage_bytes = p.stage_bytes;
+  P.wv = a.wv; P.mom = mom; P.coef = a.coef; P.y = a.y; P.bs_y = a.bs_y; P.res = a.residual ? 1.f : 0.f;
+  const int threads = 32 + p.cons_threads;
+#define MRLA_TMA_LAUNCH(CBV)                                                                              \
+  {                                                                                                       \
+    auto k = k_light_nhwc_tma<T, CBV, ACT, true, MODE>;                                                   \
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);    \
+    if (e != cudaSuccess) return (int)e;                                                                  \
+    k<<<p.grid, threads, p.smem, st>>>(tx, to, tdy, P);                                                   \
+  }
+  if (p.CB == 64) MRLA_TMA_LAUNCH(64)
+  else if (p.CB == 128) MRLA_TMA_LAUNCH(128)
+  else {
+    if (ACT == 1) return MRLA_ERR_UNSUPPORTED;
+    MRLA_TMA_LAUNCH(ACT == 1 ? 128 : 256)
+  }
+#undef MRLA_TMA_LAUNCH
+  MRLA_CHECK_LAUNCH();
+  return MRLA_OK;
+}
+
+struct TmaBwdPlan {
+  int CB, NQ, NT, WT, G, S, ncb, items, ipc, grid, cons_threads, maxslots;
+  uint32_t x_bytes, t_bytes, stage_bytes;
+  size_t smem;
+};
+
+inline bool make_tma_bwd_plan(const MrlaLightArgs& a, TmaBwdPlan* p) {
+  if (a.layout != MRLA_NHWC || a.C % 8 || a.W > 224) return false;
+  const int es = a.dtype == MRLA_F32 ? 4 : 2;
+  const int NT = (a.W + 27) / 28;
+  int WT = (a.W + NT - 1) / NT;
+  if (NT > 1) WT = (WT + 3) / 4 * 4;
+  const int NQ = (WT + kCols - 1) / kCols;
+  int CB = 0;
+  for (int cb : {256, 128, 64})
+    if (NQ * cb / 2 <= 224 && a.C % cb == 0) { CB = cb; break; }
+  if (CB == 0) CB = 64;
+  if (NQ * CB / 2 > 224) return false;
+  if (a.act == MRLA_ACT_GELU && CB == 256) CB = 128;
+  const uint32_t xrow = (uint32_t)(WT + 4) * CB * es, trow = (uint32_t)(WT + 2) * CB * es;
+  const uint32_t rowtot = xrow + 2 * trow;
+  int G;
+  if ((size_t)a.H * rowtot <= 48 * 1024) G = a.H;
+  else { G = (int)(12288 / xrow); if (G < 1) G = 1; if (G > a.H) G = a.H; }
+  p->CB = CB; p->NQ = NQ; p->NT = NT; p->WT = WT; p->G = G;
+  p->x_bytes = (uint32_t)G * xrow;
+  p->t_bytes = (uint32_t)G * trow;
+  p->stage_bytes = p->x_bytes + 2 * p->t_bytes;
+  const size_t red = (size_t)NQ * 9 * (CB / 2) * sizeof(float2);
+  int S = (int)((200 * 1024 - red) / p->stage_bytes);
+  if (S > 8) S = 8;
+  if (S < 2) return false;
+  p->S = S;
+  p->ncb = (a.C + CB - 1) / CB;
+  p->items = p->ncb * a.B * NT;
+  int grid = p->items < kNumSMs ? p->items : kNumSMs;
+  p->ipc = (p->items + grid - 1) / grid;
+  p->grid = (p->items + p->ipc - 1) / p->ipc;
+  const int ipcb = a.B * NT;
+  p->maxslots = (ipcb + p->ipc - 1) / p->ipc + 1;
+  p->cons_threads = NQ * (CB / 2);
+  p->smem = 256 + (size_t)S * p->stage_bytes + red;
+  return true;
+}
+
+template <typename T, int ACT>
+int launch_tma_bwd(const MrlaLightArgs& a, cudaStream_t st, const TmaBwdPlan& p, float* wv_part) {
+  CUtensorMap tx, tdy, to;
+  if (make_nhwc_tmap(&tx, a.x, a.dtype, a.B, a.C, a.H, a.W, a.bs_x, p.CB, p.WT + 4, p.G)) return MRLA_ERR_UNSUPPORTED;
+  if (make_nhwc_tmap(&tdy, a.dy, a.dtype, a.B, a.C, a.H, a.W, a.bs_dy, p.CB, p.WT + 2, p.G)) return MRLA_ERR_UNSUPPORTED;
+  if (make_nhwc_tmap(&to, a.o, a.dtype, a.B, a.C, a.H, a.W, a.bs_o, p.CB, p.WT + 2, p.G)) return MRLA_ERR_UNSUPPORTED;
+  cudaError_t e = cudaMemsetAsync(wv_part, 0, (size_t)p.maxslots * a.C * 9 * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  TmaBwdParams P;
+  P.B = a.B; P.C = a.C; P.H = a.H; P.W = a.W;
+  P.G = p.G; P.S = p.S; P.NQ = p.NQ; P.ncb = p.ncb; P.NT = p.NT; P.WT = p.WT; P.items = p.items; P.ipc = p.ipc;
+  P.cons_threads = p.cons_threads; P.maxslots = p.maxslots;
+  P.x_bytes = p.x_bytes; P.t_bytes = p.t_bytes; P.stage_bytes = p.stage_bytes;
+  P.wv = a.wv; P.lam = a.lam; P.bcoef = a.bcoef; P.dx = a.dx; P.dout = a.dout; P.bs_dx = a.bs_dx; P.bs_do = a.bs_do;
+  P.res = a.residual ? 1.f : 0.f; P.wv_part = wv_part;
+  const int threads = 32 + p.cons_threads;
+#define MRLA_TMA_LAUNCH(CBV)                                                                              \
+  {                                                                                                       \
+    auto k = k_light_nhwc_tma_bwd<T, CBV, ACT>;                                                           \
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);                \
+    if (e != cudaSuccess) return (int)e;                                                                  \
+    k<<<p.grid, threads, p.smem, st>>>(tx, tdy, to, P);                                                   \
+  }
+  if (p.CB == 64) MRLA_TMA_LAUNCH(64)
+  else if (p.CB == 128) MRLA_TMA_LAUNCH(128)
+  else {
+    if (ACT == 1) return MRLA_ERR_UNSUPPORTED;
+    MRLA_TMA_LAUNCH(ACT == 1 ? 128 : 256)
+  }
+#undef MRLA_TMA_LAUNCH
+  MRLA_CHECK_LAUNCH();
+  return MRLA_OK;
+}
+
 // ------------------------------------------------------------------------------------ forward
 template <typename T, int LAYOUT, int CV, int ACT, bool HAS_O>
 int light_forward_impl(const MrlaLightArgs& a, cudaStream_t st) {
@@ -81,8 +239,15 @@ int light_forward_impl(const MrlaLightArgs& a, cudaStream_t st) {
   const T* x = static_cast<const T*>(a.x);
   const T* o = static_cast<const T*>(a.o);
   T* y = static_cast<T*>(a.y);
+  const int es = a.dtype == MRLA_F32 ? 4 : 2;
+  TmaPlan tp1, tp2;
+  const bool tma_ok = LAYOUT == MRLA_NHWC && HAS_O && tma_ptr_ok(a.x, a.bs_x, es) && tma_ptr_ok(a.o, a.bs_o, es) &&
+                      (a.bs_y * es) % 4 == 0 && make_tma_plan(a, 1, 6, &tp1) && make_tma_plan(a, 1, 0, &tp2);
   // sweep 1
-  {
+  if (tma_ok && full) {
+    rc = launch_tma_sweep<T, ACT, 0>(a, st, tp1, a.x, a.bs_x, a.o, a.bs_o, nullptr, 0, a.mom);
+    if (rc) return rc;
+  } else {
     const int nm = full ? (HAS_O ? 6 : 3) : 1;
     const size_t sm = (size_t)p.threads * nm * CV * sizeof(float);
     if (full) {
@@ -107,7 +272,10 @@ int light_forward_impl(const MrlaLightArgs& a, cudaStream_t st) {
     MRLA_CHECK_LAUNCH();
   }
   // sweep 2
-  {
+  if (tma_ok) {
+    rc = launch_tma_sweep<T, ACT, 1>(a, st, tp2, a.x, a.bs_x, a.o, a.bs_o, nullptr, 0, nullptr);
+    if (rc) return rc;
+  } else {
     auto k = k_light_apply_fwd<T, LAYOUT, CV, ACT, HAS_O>;
     k<<<grid, p.threads, 0, st>>>(x, o, y, a.wv, a.coef, s, a.bs_x, a.bs_o, a.bs_y, a.residual ? 1.f : 0.f);
     MRLA_CHECK_LAUNCH();
@@ -126,18 +294,31 @@ int light_backward_impl(const MrlaLightArgs& a, cudaStream_t st) {
   if (rc) return rc;
   rc = make_plan(LAYOUT, a.B, a.C, a.W, CVB, &pb);
   if (rc) return rc;
-  const size_t need = ((size_t)pb.grid_y * a.C * 9 + (size_t)a.B * 2 * a.k_size) * sizeof(float);
+  const int es_ = a.dtype == MRLA_F32 ? 4 : 2;
+  TmaBwdPlan tpb;
+  const bool tma_b = LAYOUT == MRLA_NHWC && HAS_O && tma_ptr_ok(a.x, a.bs_x, es_) && tma_ptr_ok(a.o, a.bs_o, es_) &&
+                     tma_ptr_ok(a.dy, a.bs_dy, es_) && (a.bs_dx * es_) % 4 == 0 && (a.bs_do * es_) % 4 == 0 &&
+                     make_tma_bwd_plan(a, &tpb);
+  const int nparts = tma_b ? tpb.maxslots : pb.grid_y;
+  const size_t need = ((size_t)nparts * a.C * 9 + (size_t)a.B * 2 * a.k_size) * sizeof(float);
   if (a.scratch == nullptr || a.scratch_bytes < need) return MRLA_ERR_WORKSPACE;
   float* wv_part = a.scratch;
-  float* wqk_part = a.scratch + (size_t)pb.grid_y * a.C * 9;
+  float* wqk_part = a.scratch + (size_t)nparts * a.C * 9;
   const bool full = (a.bn_mode == MRLA_BN_TRAIN);
   const T* x = static_cast<const T*>(a.x);
   const T* o = static_cast<const T*>(a.o);
   const T* dy = static_cast<const T*>(a.dy);
   T* dx = static_cast<T*>(a.dx);
   T* dout = static_cast<T*>(a.dout);
+  const int es = a.dtype == MRLA_F32 ? 4 : 2;
+  TmaPlan tpa;
+  const bool tma_ok = LAYOUT == MRLA_NHWC && HAS_O && tma_ptr_ok(a.x, a.bs_x, es) && tma_ptr_ok(a.o, a.bs_o, es) &&
+                      tma_ptr_ok(a.dy, a.bs_dy, es) && make_tma_plan(a, 2, 3, &tpa);
   // sweep A
-  {
+  if (tma_ok) {
+    rc = launch_tma_sweep<T, ACT, 2>(a, st, tpa, a.x, a.bs_x, a.o, a.bs_o, a.dy, a.bs_dy, a.gmom);
+    if (rc) return rc;
+  } else {
     SweepShape s{a.B, a.C, a.H, a.W, p.slots};
     const int nm = HAS_O ? 3 : 2;
     const size_t sm = (size_t)p.threads * nm * CV * sizeof(float);
@@ -161,7 +342,10 @@ int light_backward_impl(const MrlaLightArgs& a, cudaStream_t st) {
     MRLA_CHECK_LAUNCH();
   }
   // sweep B
-  {
+  if (tma_b) {
+    rc = launch_tma_bwd<T, ACT>(a, st, tpb, wv_part);
+    if (rc) return rc;
+  } else {
     SweepShape s{a.B, a.C, a.H, a.W, pb.slots};
     const size_t sm = (size_t)pb.threads * 9 * CVB * sizeof(float);
     auto k = k_light_apply_bwd<T, LAYOUT, CVB, ACT, HAS_O>;
@@ -175,7 +359,7 @@ int light_backward_impl(const MrlaLightArgs& a, cudaStream_t st) {
   // final reductions
   {
     const int total = a.C * 9 + 2 * a.k_size;
-    k_light_finish<<<(total + 255) / 256, 256, 0, st>>>(wv_part, pb.grid_y, wqk_part, a.dwv, a.dwq, a.dwk, a.B, a.C,
+    k_light_finish<<<(total + 255) / 256, 256, 0, st>>>(wv_part, nparts, wqk_part, a.dwv, a.dwq, a.dwk, a.B, a.C,
                                                          a.k_size);
     MRLA_CHECK_LAUNCH();
   }
@@ -211,7 +395,10 @@ inline size_t light_bwd_scratch_floats(const MrlaLightArgs& a) {
   LightPlan pb;
   const int cvb = a.layout == MRLA_NCHW ? 1 : 2;
   if (make_plan(a.layout, a.B, a.C, a.W, cvb, &pb)) return 0;
-  return (size_t)pb.grid_y * a.C * 9 + (size_t)a.B * 2 * a.k_size;
+  int nparts = pb.grid_y;
+  TmaBwdPlan tpb;
+  if (make_tma_bwd_plan(a, &tpb) && tpb.maxslots > nparts) nparts = tpb.maxslots;
+  return (size_t)nparts * a.C * 9 + (size_t)a.B * 2 * a.k_size;
 }
 
 }  // namespace mrla

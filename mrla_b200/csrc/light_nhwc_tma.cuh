@@ -1,0 +1,588 @@
+// v2 NHWC sweeps of the MRLA-light tail: TMA-fed shared-memory row ring + packed fp32x2 math.
+//
+// One CTA = 1 producer warp + NQ*(CB/2) consumer threads, persistent over work items (b, channel block).
+//   producer : one elected lane streams the image in groups of G rows with cp.async.bulk.tensor (TMA):
+//              x box = [CB ch, W+2 cols (from w=-1), G rows]  — out-of-bounds columns / rows / channels are
+//              zero-filled by the TMA unit, which IS the conv zero padding;  o / dy box = [CB, W, G].
+//              S stages, full/empty mbarriers, up to ~190 KB in flight per SM.
+//   consumers: thread = (channel pair p, column group q of 4 columns); lanes of a warp are 32 consecutive
+//              channel pairs (128 B of one pixel -> conflict-free LDS.32).  Each thread marches down the rows
+//              with a 3-row x 6-column register window of fp32x2 pairs; every x row is read from shared
+//              memory exactly once per thread and the depthwise 3x3 is 9 FFMA2 per output pair.
+// Replaces (paths relative to /root/reference) mrla_light_module.py:56-72, resnet_mrla_light.py:42,116.
+#pragma once
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace mrla {
+
+constexpr int kCols = 4;          // output columns per consumer thread
+constexpr int kWin = kCols + 2;   // window columns (one halo column each side)
+
+struct TmaSweepParams {
+  int B, C, H, W;
+  int G, S, NQ, ncb, items;
+  int cons_threads;
+  uint32_t x_bytes, o_bytes, stage_bytes;   // per stage (x tile, o/dy tile, total)
+  const float* wv;      // [C,9]
+  float* mom;           // MODE 0: [6,B,C] ; MODE 2: gmom [3,B,C]
+  const float* coef;    // MODE 1: [3,B,C]
+  void* y;              // MODE 1
+  int64_t bs_y;
+  float res;
+};
+
+// ---------------------------------------------------------------------------- packed helpers
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+
+template <typename T> __device__ __forceinline__ float2 lds_pair(uint32_t saddr);
+template <> __device__ __forceinline__ float2 lds_pair<__nv_bfloat16>(uint32_t saddr) {
+  uint32_t u;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(saddr));
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+template <> __device__ __forceinline__ float2 lds_pair<__half>(uint32_t saddr) {
+  uint32_t u;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(saddr));
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+template <> __device__ __forceinline__ float2 lds_pair<float>(uint32_t saddr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
+  return v;
+}
+template <typename T> __device__ __forceinline__ void stg_pair(T* p, float2 v);
+template <> __device__ __forceinline__ void stg_pair<__nv_bfloat16>(__nv_bfloat16* p, float2 v) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y);
+}
+template <> __device__ __forceinline__ void stg_pair<__half>(__half* p, float2 v) {
+  *reinterpret_cast<__half2*>(p) = __floats2half2_rn(v.x, v.y);
+}
+template <> __device__ __forceinline__ void stg_pair<float>(float* p, float2 v) {
+  *reinterpret_cast<float2*>(p) = v;
+}
+
+template <int ACT> __device__ __forceinline__ float2 act2(float2 u) {
+  if (ACT == 1) return make_float2(act_fwd<1>(u.x), act_fwd<1>(u.y));
+  return u;
+}
+
+// 3x3 depthwise taps on one output column `j` of the window (w9[i*3+dj] are channel-pair weights)
+__device__ __forceinline__ float2 conv9(const float2 (&top)[kWin], const float2 (&mid)[kWin], const float2 (&bot)[kWin],
+                                        const float2 (&w9)[9], int j) {
+  float2 s = fmul2(w9[0], top[j]);
+  s = ffma2(w9[1], top[j + 1], s);
+  s = ffma2(w9[2], top[j + 2], s);
+  s = ffma2(w9[3], mid[j], s);
+  s = ffma2(w9[4], mid[j + 1], s);
+  s = ffma2(w9[5], mid[j + 2], s);
+  s = ffma2(w9[6], bot[j], s);
+  s = ffma2(w9[7], bot[j + 1], s);
+  s = ffma2(w9[8], bot[j + 2], s);
+  return s;
+}
+
+// ---------------------------------------------------------------------------- the kernel
+// MODE 0: forward moments (Σx ΣV ΣV² [ΣVo Σo Σo²]) ; MODE 1: forward apply (y) ; MODE 2: backward moments (Σdy ΣdyV [Σdyo])
+template <typename T, int CB, int ACT, bool HAS_O, int MODE>
+__global__ void __launch_bounds__(480, 1)
+k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_o,
+                 const __grid_constant__ CUtensorMap tm_dy, TmaSweepParams P) {
+  constexpr int NP = CB / 2;                                  // channel pairs per block
+  constexpr int NACC = (MODE == 0) ? (HAS_O ? 6 : 3) : (MODE == 2 ? (HAS_O ? 3 : 2) : 0);
+  constexpr bool HAS_DY = (MODE == 2);
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + 16;
+  unsigned char* stages = smem_raw + 256;
+  float2* red = reinterpret_cast<float2*>(stages + (size_t)P.S * P.stage_bytes);  // [NQ][NACC][NP]
+  const int ncw = P.cons_threads / 32;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], ncw);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const int ngroups = (P.H + P.G - 1) / P.G;
+
+  if (threadIdx.x < 32) {
+    // ================================ producer warp ================================
+    if (threadIdx.x == 0) {
+      tma_prefetch_desc(&tm_x);
+      if (HAS_O) tma_prefetch_desc(&tm_o);
+      if (HAS_DY) tma_prefetch_desc(&tm_dy);
+      int st = 0;
+      uint32_t ph = 1;  // first pass over the ring: slots are free
+      for (int item = blockIdx.x; item < P.items; item += gridDim.x) {
+        const int b = item / P.ncb, cb = item - b * P.ncb;
+        for (int g = 0; g < ngroups; ++g) {
+          mbar_wait(&empty[st], ph);
+          unsigned char* sx = stages + (size_t)st * P.stage_bytes;
+          mbar_arrive_expect_tx(&full[st], P.stage_bytes);
+          tma_load_4d(sx, &tm_x, &full[st], cb * CB, -1, g * P.G, b);
+          if (HAS_O) tma_load_4d(sx + P.x_bytes, &tm_o, &full[st], cb * CB, 0, g * P.G, b);
+          if (HAS_DY) tma_load_4d(sx + P.x_bytes + (HAS_O ? P.o_bytes : 0), &tm_dy, &full[st], cb * CB, 0, g * P.G, b);
+          if (++st == P.S) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ================================== consumers ==================================
+  const int ct = threadIdx.x - 32;
+  const int p = ct % NP, q = ct / NP;
+  const int lane = threadIdx.x & 31;
+  constexpr int ES = sizeof(T);
+  const uint32_t stages_s = smem_u32(stages);
+  const uint32_t xrow_bytes = (uint32_t)(P.W + 2) * CB * ES;
+  const uint32_t orow_bytes = (uint32_t)P.W * CB * ES;
+  // shared-memory byte offsets of this thread's window / output columns inside a tile row
+  uint32_t xoff[kWin], ooff[kCols];
+  float2 cmask[kCols];
+  bool cvalid[kCols];
+#pragma unroll
+  for (int j = 0; j < kWin; ++j) {
+    int sc = q * kCols + j;  // smem column index = image column + 1
+    if (sc > P.W + 1) sc = P.W + 1;
+    xoff[j] = (uint32_t)sc * CB * ES + (uint32_t)p * 2 * ES;
+  }
+#pragma unroll
+  for (int j = 0; j < kCols; ++j) {
+    const int col = q * kCols + j;
+    cvalid[j] = col < P.W;
+    cmask[j] = cvalid[j] ? f2(1.f, 1.f) : f2(0.f, 0.f);
+    ooff[j] = (uint32_t)(cvalid[j] ? col : P.W - 1) * CB * ES + (uint32_t)p * 2 * ES;
+  }
+
+  int st_cur = 0;        // stage of the group that holds x row r
+  uint32_t ph_cur = 0;
+  int st_prev = 0;       // stage of the group that holds row r-1
+
+  for (int item = blockIdx.x; item < P.items; item += gridDim.x) {
+    const int b = item / P.ncb, cb = item - b * P.ncb;
+    const int c = cb * CB + 2 * p;
+    const bool chan_ok = c < P.C;
+    float2 w9[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+      w9[i] = chan_ok ? f2(P.wv[(int64_t)c * 9 + i], P.wv[(int64_t)(c + 1) * 9 + i]) : f2(0.f, 0.f);
+    float2 cA = f2(0.f, 0.f), cL = f2(0.f, 0.f), cD = f2(0.f, 0.f);
+    if (MODE == 1 && chan_ok) {
+      const int64_t BC = (int64_t)P.B * P.C;
+      const float* cp = P.coef + (int64_t)b * P.C + c;
+      cA = *reinterpret_cast<const float2*>(cp);
+      if (HAS_O) cL = *reinterpret_cast<const float2*>(cp + BC);
+      cD = *reinterpret_cast<const float2*>(cp + 2 * BC);
+    }
+    const float2 res2 = f2(P.res, P.res);
+    float2 acc[NACC > 0 ? NACC : 1];
+#pragma unroll
+    for (int i = 0; i < (NACC > 0 ? NACC : 1); ++i) acc[i] = f2(0.f, 0.f);
+    T* yb = (MODE == 1) ? static_cast<T*>(P.y) + (int64_t)b * P.bs_y + c : nullptr;
+
+    float2 win[3][kWin];
+#pragma unroll
+    for (int j = 0; j < kWin; ++j) win[2][j] = f2(0.f, 0.f);  // row -1 lives in slot 2
+
+    int rr = 0;  // row index of r inside its group
+    // r = x row being fetched into the window; output row r-1 is produced in the same step
+    for (int r0 = 0; r0 <= P.H; r0 += 3) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int r = r0 + i;
+        if (r <= P.H) {
+          // ---- fetch x row r into window slot i ----
+          if (r < P.H) {
+            if (rr == 0) mbar_wait(&full[st_cur], ph_cur);
+            const uint32_t rowb = stages_s + (uint32_t)st_cur * P.stage_bytes + (uint32_t)rr * xrow_bytes;
+#pragma unroll
+            for (int j = 0; j < kWin; ++j) win[i][j] = lds_pair<T>(rowb + xoff[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kWin; ++j) win[i][j] = f2(0.f, 0.f);
+          }
+          // ---- produce output row r-1 ----
+          if (r >= 1) {
+            const int ro = r - 1;
+            const int rro = (rr == 0) ? (P.G - 1) : rr - 1;           // its row inside its group
+            const int sto = (rr == 0) ? st_prev : st_cur;
+            const int rro_fix = (r == P.H) ? ((P.H - 1) % P.G) : rro;  // last image row may sit in a short group
+            const int sto_fix = (r == P.H) ? st_prev : sto;
+            const uint32_t ob = stages_s + (uint32_t)sto_fix * P.stage_bytes + P.x_bytes + (uint32_t)rro_fix * orow_bytes;
+            const float2(&top)[kWin] = win[(i + 1) % 3];
+            const float2(&mid)[kWin] = win[(i + 2) % 3];
+            const float2(&bot)[kWin] = win[i];
+#pragma unroll
+            for (int j = 0; j < kCols; ++j) {
+              float2 u = conv9(top, mid, bot, w9, j);
+              float2 v = act2<ACT>(u);
+              float2 ov = f2(0.f, 0.f), gv = f2(0.f, 0.f);
+              if (HAS_O) ov = fmul2(lds_pair<T>(ob + ooff[j]), cmask[j]);
+              if (HAS_DY) gv = fmul2(lds_pair<T>(ob + (HAS_O ? P.o_bytes : 0) + ooff[j]), cmask[j]);
+              const float2 xc = mid[j + 1];
+              if (MODE == 0) {
+                v = fmul2(v, cmask[j]);
+                acc[0] = fadd2(acc[0], xc);
+                acc[1] = fadd2(acc[1], v);
+                acc[2] = ffma2(v, v, acc[2]);
+                if (HAS_O) {
+                  acc[3] = ffma2(v, ov, acc[3]);
+                  acc[4] = fadd2(acc[4], ov);
+                  acc[5] = ffma2(ov, ov, acc[5]);
+                }
+              } else if (MODE == 2) {
+                acc[0] = fadd2(acc[0], gv);
+                acc[1] = ffma2(gv, v, acc[1]);
+                if (HAS_O) acc[2] = ffma2(gv, ov, acc[2]);
+              } else {
+                float2 t = ffma2(cA, v, cD);
+                if (HAS_O) t = ffma2(cL, ov, t);
+                t = ffma2(res2, xc, t);
+                if (chan_ok && cvalid[j]) stg_pair<T>(yb + ((int64_t)ro * P.W + (q * kCols + j)) * P.C, t);
+              }
+            }
+            // release the group whose last row was just consumed
+            if (rro_fix == P.G - 1 || ro == P.H - 1) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&empty[sto_fix]);
+            }
+          }
+          // ---- advance the row-in-group cursor ----
+          if (r < P.H) {
+            if (++rr == P.G || r == P.H - 1) {
+              rr = 0;
+              st_prev = st_cur;
+              if (++st_cur == P.S) { st_cur = 0; ph_cur ^= 1; }
+            }
+          }
+        }
+      }
+    }
+
+    if (NACC > 0) {
+      // deterministic reduction over the NQ column groups of every channel pair
+#pragma unroll
+      for (int i = 0; i < NACC; ++i) red[((size_t)q * NACC + i) * NP + p] = acc[i];
+      named_bar_sync(1, P.cons_threads);
+      const int64_t BC = (int64_t)P.B * P.C;
+      for (int idx = ct; idx < NACC * NP; idx += P.cons_threads) {
+        const int mi = idx / NP, pp = idx - mi * NP;
+        float2 s = f2(0.f, 0.f);
+        for (int qq = 0; qq < P.NQ; ++qq) {
+          const float2 v = red[((size_t)qq * NACC + mi) * NP + pp];
+          s.x += v.x;
+          s.y += v.y;
+        }
+        const int cc = cb * CB + 2 * pp;
+        if (cc < P.C) *reinterpret_cast<float2*>(P.mom + (int64_t)mi * BC + (int64_t)b * P.C + cc) = s;
+      }
+      named_bar_sync(1, P.cons_threads);
+    }
+  }
+}
+
+
+// =====================================================================================================
+// v2 sweep B (backward apply), NHWC:   dS = Q0 + Q1*dy + Q2*V + Q3*o ;  T = Ta*dS*act'(U)
+//     do = lam*dS ;  dx = res*dy + dwconv3x3^T(T) + dyc ;  dWv[c,i,j] = Σ T[h,w]*x[h+i-1,w+j-1]
+// Work item = (channel block, sample, column tile of WT<=28 columns).  A consumer thread owns 4 output
+// columns of one channel pair and recomputes T on one halo column each side (x window = 3 rows x 8 cols),
+// so the transposed conv needs no exchange between threads; dX rows are built in scatter form with three
+// rotating row accumulators.  CTAs take CONTIGUOUS item ranges ordered (cb, b, tile) so the dWv partial
+// sums stay in registers across samples and are flushed once per channel block into
+// wv_part[slot][C][9] (slot = CTA index relative to the first CTA touching that channel block).
+struct TmaBwdParams {
+  int B, C, H, W;
+  int G, S, NQ, ncb, NT, WT, items, ipc, cons_threads, maxslots;
+  uint32_t x_bytes, t_bytes, stage_bytes;
+  const float* wv;
+  const float* lam;
+  const float* bcoef;  // [7,B,C]
+  void* dx;
+  void* dout;
+  int64_t bs_dx, bs_do;
+  float res;
+  float* wv_part;      // [maxslots, C, 9]
+};
+
+template <typename T, int CB, int ACT>
+__global__ void __launch_bounds__(256, 1)
+k_light_nhwc_tma_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy,
+                     const __grid_constant__ CUtensorMap tm_o, TmaBwdParams P) {
+  constexpr int NP = CB / 2;
+  constexpr int XW = kCols + 4;  // x window columns
+  constexpr int TW = kCols + 2;  // T columns
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + 16;
+  unsigned char* stages = smem_raw + 256;
+  float2* red = reinterpret_cast<float2*>(stages + (size_t)P.S * P.stage_bytes);  // [NQ][9][NP]
+  const int ncw = P.cons_threads / 32;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], ncw);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int ngroups = (P.H + P.G - 1) / P.G;
+  const int item_beg = blockIdx.x * P.ipc;
+  const int item_end = min(item_beg + P.ipc, P.items);
+  const int ipcb = P.B * P.NT;  // items per channel block
+
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0) {
+      tma_prefetch_desc(&tm_x);
+      tma_prefetch_desc(&tm_dy);
+      tma_prefetch_desc(&tm_o);
+      int st = 0;
+      uint32_t ph = 1;
+      for (int item = item_beg; item < item_end; ++item) {
+        const int cb = item / ipcb;
+        const int rem = item - cb * ipcb;
+        const int b = rem / P.NT, tile = rem - b * P.NT;
+        const int w0 = tile * P.WT;
+        for (int g = 0; g < ngroups; ++g) {
+          mbar_wait(&empty[st], ph);
+          unsigned char* sx = stages + (size_t)st * P.stage_bytes;
+          mbar_arrive_expect_tx(&full[st], P.stage_bytes);
+          tma_load_4d(sx, &tm_x, &full[st], cb * CB, w0 - 2, g * P.G, b);
+          tma_load_4d(sx + P.x_bytes, &tm_dy, &full[st], cb * CB, w0 - 1, g * P.G, b);
+          tma_load_4d(sx + P.x_bytes + P.t_bytes, &tm_o, &full[st], cb * CB, w0 - 1, g * P.G, b);
+          if (++st == P.S) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+    return;
+  }
+
+  const int ct = threadIdx.x - 32;
+  const int p = ct % NP, q = ct / NP;
+  const int lane = threadIdx.x & 31;
+  constexpr int ES = sizeof(T);
+  const uint32_t stages_s = smem_u32(stages);
+  const uint32_t xrow_bytes = (uint32_t)(P.WT + 4) * CB * ES;
+  const uint32_t trow_bytes = (uint32_t)(P.WT + 2) * CB * ES;
+  uint32_t xoff[XW], toff[TW];
+#pragma unroll
+  for (int k = 0; k < XW; ++k) {
+    int sc = q * kCols + k;
+    if (sc > P.WT + 3) sc = P.WT + 3;
+    xoff[k] = (uint32_t)sc * CB * ES + (uint32_t)p * 2 * ES;
+  }
+#pragma unroll
+  for (int j = 0; j < TW; ++j) {
+    int sc = q * kCols + j;
+    if (sc > P.WT + 1) sc = P.WT + 1;
+    toff[j] = (uint32_t)sc * CB * ES + (uint32_t)p * 2 * ES;
+  }
+
+  int st_cur = 0, st_prev = 0;
+  uint32_t ph_cur = 0;
+  int cur_cb = -1;
+  float2 dw[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) dw[i] = f2(0.f, 0.f);
+  float2 w9[9];
+  float2 lm = f2(0.f, 0.f);
+  const int64_t BC = (int64_t)P.B * P.C;
+
+  auto flush_dw = [&](int cb) {
+    // reduce dw over the NQ column groups, write this CTA's partial for channel block `cb`
+#pragma unroll
+    for (int i = 0; i < 9; ++i) red[((size_t)q * 9 + i) * NP + p] = dw[i];
+    named_bar_sync(1, P.cons_threads);
+    const int first_cta = (cb * ipcb) / P.ipc;
+    const int slot = blockIdx.x - first_cta;
+    for (int idx = ct; idx < 9 * NP; idx += P.cons_threads) {
+      const int tap = idx / NP, pp = idx - tap * NP;
+      float2 s = f2(0.f, 0.f);
+      for (int qq = 0; qq < P.NQ; ++qq) {
+        const float2 v = red[((size_t)qq * 9 + tap) * NP + pp];
+        s.x += v.x;
+        s.y += v.y;
+      }
+      const int cc = cb * CB + 2 * pp;
+      if (cc < P.C) {
+        float* dst = P.wv_part + ((int64_t)slot * P.C + cc) * 9 + tap;
+        dst[0] = s.x;    // each (slot, channel block) is written by exactly one CTA, exactly once;
+        dst[9] = s.y;    // slots no CTA maps to stay at their memset zero
+      }
+    }
+    named_bar_sync(1, P.cons_threads);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) dw[i] = f2(0.f, 0.f);
+  };
+
+  for (int item = item_beg; item < item_end; ++item) {
+    const int cb = item / ipcb;
+    const int rem = item - cb * ipcb;
+    const int b = rem / P.NT, tile = rem - b * P.NT;
+    const int w0 = tile * P.WT;
+    const int wt = min(P.WT, P.W - w0);
+    const int c = cb * CB + 2 * p;
+    const bool chan_ok = c < P.C;
+    if (cb != cur_cb) {
+      if (cur_cb >= 0) flush_dw(cur_cb);
+      cur_cb = cb;
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+        w9[i] = chan_ok ? f2(P.wv[(int64_t)c * 9 + i], P.wv[(int64_t)(c + 1) * 9 + i]) : f2(0.f, 0.f);
+      lm = (chan_ok && P.lam) ? f2(P.lam[c], P.lam[c + 1]) : f2(0.f, 0.f);
+    }
+    float2 q0 = f2(0.f, 0.f), q1 = q0, q2 = q0, q3 = q0, ta = q0, dyc = q0;
+    if (chan_ok) {
+      const float* cp = P.bcoef + (int64_t)b * P.C + c;
+      q0 = *reinterpret_cast<const float2*>(cp);
+      q1 = *reinterpret_cast<const float2*>(cp + BC);
+      q2 = *reinterpret_cast<const float2*>(cp + 2 * BC);
+      q3 = *reinterpret_cast<const float2*>(cp + 3 * BC);
+      ta = *reinterpret_cast<const float2*>(cp + 4 * BC);
+      dyc = *reinterpret_cast<const float2*>(cp + 5 * BC);
+    }
+    const float2 res2 = f2(P.res, P.res);
+    bool tvalid[TW], ovalid[kCols];
+#pragma unroll
+    for (int j = 0; j < TW; ++j) {
+      const int col = w0 + q * kCols - 1 + j;
+      tvalid[j] = col >= 0 && col < P.W;
+    }
+#pragma unroll
+    for (int j = 0; j < kCols; ++j) ovalid[j] = chan_ok && (q * kCols + j < wt);
+    T* dxb = static_cast<T*>(P.dx) + (int64_t)b * P.bs_dx + (int64_t)(w0 + q * kCols) * P.C + c;
+    T* dob = static_cast<T*>(P.dout) + (int64_t)b * P.bs_do + (int64_t)(w0 + q * kCols) * P.C + c;
+    const int64_t row_stride = (int64_t)P.W * P.C;
+
+    float2 xw[3][XW];
+    float2 da[3][kCols];   // rotating dX row accumulators: row t lives in slot t % 3
+    float2 dyprev[kCols];
+#pragma unroll
+    for (int k = 0; k < XW; ++k) xw[2][k] = f2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < kCols; ++j) {
+      da[0][j] = f2(0.f, 0.f); da[1][j] = f2(0.f, 0.f); da[2][j] = f2(0.f, 0.f);
+      dyprev[j] = f2(0.f, 0.f);
+    }
+    int rr = 0;
+    for (int r0 = 0; r0 <= P.H; r0 += 3) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int r = r0 + i;
+        if (r <= P.H) {
+          if (r < P.H) {
+            if (rr == 0) mbar_wait(&full[st_cur], ph_cur);
+            const uint32_t rowb = stages_s + (uint32_t)st_cur * P.stage_bytes + (uint32_t)rr * xrow_bytes;
+#pragma unroll
+            for (int k = 0; k < XW; ++k) xw[i][k] = lds_pair<T>(rowb + xoff[k]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < XW; ++k) xw[i][k] = f2(0.f, 0.f);
+          }
+          if (r >= 1) {
+            const int t = r - 1;                                     // T row produced in this step
+            const int rro = (r == P.H) ? ((P.H - 1) % P.G) : ((rr == 0) ? (P.G - 1) : rr - 1);
+            const int sto = (r == P.H || rr == 0) ? st_prev : st_cur;
+            const uint32_t tb = stages_s + (uint32_t)sto * P.stage_bytes + P.x_bytes + (uint32_t)rro * trow_bytes;
+            const float2(&top)[XW] = xw[(i + 1) % 3];
+            const float2(&mid)[XW] = xw[(i + 2) % 3];
+            const float2(&bot)[XW] = xw[i];
+            float2 tn[TW];
+            float2 dyc_row[kCols];
+#pragma unroll
+            for (int j = 0; j < TW; ++j) {
+              float2 u = fmul2(w9[0], top[j]);
+              u = ffma2(w9[1], top[j + 1], u);
+              u = ffma2(w9[2], top[j + 2], u);
+              u = ffma2(w9[3], mid[j], u);
+              u = ffma2(w9[4], mid[j + 1], u);
+              u = ffma2(w9[5], mid[j + 2], u);
+              u = ffma2(w9[6], bot[j], u);
+              u = ffma2(w9[7], bot[j + 1], u);
+              u = ffma2(w9[8], bot[j + 2], u);
+              const float2 v = act2<ACT>(u);
+              const float2 gy = lds_pair<T>(tb + toff[j]);
+              const float2 ov = lds_pair<T>(tb + P.t_bytes + toff[j]);
+              float2 ds = ffma2(q1, gy, q0);
+              ds = ffma2(q2, v, ds);
+              ds = ffma2(q3, ov, ds);
+              float2 tt = fmul2(ta, ds);
+              if (ACT == 1) tt = fmul2(tt, f2(act_grad<1>(u.x), act_grad<1>(u.y)));
+              tn[j] = tvalid[j] ? tt : f2(0.f, 0.f);
+              if (j >= 1 && j <= kCols) {
+                const int jo = j - 1;
+                dyc_row[jo] = gy;
+                if (ovalid[jo]) stg_pair<T>(dob + (int64_t)t * row_stride + (int64_t)jo * P.C, fmul2(lm, ds));
+                // dWv[i][dj] += T[t][w] * x[t+i-1][w+dj-1]  (x window index = j + dj)
+                dw[0] = ffma2(tn[j], top[j], dw[0]);
+                dw[1] = ffma2(tn[j], top[j + 1], dw[1]);
+                dw[2] = ffma2(tn[j], top[j + 2], dw[2]);
+                dw[3] = ffma2(tn[j], mid[j], dw[3]);
+                dw[4] = ffma2(tn[j], mid[j + 1], dw[4]);
+                dw[5] = ffma2(tn[j], mid[j + 2], dw[5]);
+                dw[6] = ffma2(tn[j], bot[j], dw[6]);
+                dw[7] = ffma2(tn[j], bot[j + 1], dw[7]);
+                dw[8] = ffma2(tn[j], bot[j + 2], dw[8]);
+              }
+            }
+            // scatter T[t] into dX rows t-1 (taps i=0), t (i=1), t+1 (i=2, first contribution)
+            // dX[h][w] += wv[i][jj] * T[h-i+1][w-jj+1]  ->  T index for own column jo: jo + 2 - jj
+            float2(&a_m1)[kCols] = da[(i + 1) % 3];   // row t-1 = r-2
+            float2(&a_0)[kCols] = da[(i + 2) % 3];    // row t   = r-1
+            float2(&a_p1)[kCols] = da[i];             // row t+1 = r
+#pragma unroll
+            for (int jo = 0; jo < kCols; ++jo) {
+              a_m1[jo] = ffma2(w9[0], tn[jo + 2], a_m1[jo]);
+              a_m1[jo] = ffma2(w9[1], tn[jo + 1], a_m1[jo]);
+              a_m1[jo] = ffma2(w9[2], tn[jo], a_m1[jo]);
+              a_0[jo] = ffma2(w9[3], tn[jo + 2], a_0[jo]);
+              a_0[jo] = ffma2(w9[4], tn[jo + 1], a_0[jo]);
+              a_0[jo] = ffma2(w9[5], tn[jo], a_0[jo]);
+              float2 n = fmul2(w9[6], tn[jo + 2]);
+              n = ffma2(w9[7], tn[jo + 1], n);
+              a_p1[jo] = ffma2(w9[8], tn[jo], n);
+            }
+            if (t >= 1) {
+#pragma unroll
+              for (int jo = 0; jo < kCols; ++jo) {
+                const float2 out = fadd2(ffma2(res2, dyprev[jo], dyc), a_m1[jo]);
+                if (ovalid[jo]) stg_pair<T>(dxb + (int64_t)(t - 1) * row_stride + (int64_t)jo * P.C, out);
+              }
+            }
+            if (t == P.H - 1) {
+#pragma unroll
+              for (int jo = 0; jo < kCols; ++jo) {
+                const float2 out = fadd2(ffma2(res2, dyc_row[jo], dyc), a_0[jo]);
+                if (ovalid[jo]) stg_pair<T>(dxb + (int64_t)t * row_stride + (int64_t)jo * P.C, out);
+              }
+            }
+#pragma unroll
+            for (int jo = 0; jo < kCols; ++jo) dyprev[jo] = dyc_row[jo];
+            if (rro == P.G - 1 || t == P.H - 1) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&empty[sto]);
+            }
+          }
+          if (r < P.H) {
+            if (++rr == P.G || r == P.H - 1) {
+              rr = 0;
+              st_prev = st_cur;
+              if (++st_cur == P.S) { st_cur = 0; ph_cur ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  }
+  if (cur_cb >= 0) flush_dw(cur_cb);
+}
+
+}  // namespace mrla
