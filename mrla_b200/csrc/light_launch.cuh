@@ -89,7 +89,7 @@ inline bool make_tma_plan(const MrlaLightArgs& a, int ntiles, int nacc, TmaPlan*
     if (NQ * 32 <= 448) CB = 64; else return false;
   }
   if (a.act == MRLA_ACT_GELU && CB == 256) CB = 128;
-  const uint32_t xrow = (uint32_t)(a.W + 2) * CB * es, orow = (uint32_t)a.W * CB * es;
+  const uint32_t xrow = (uint32_t)(NQ * kCols + 2) * CB * es, orow = (uint32_t)(NQ * kCols) * CB * es;
   int G;
   if ((size_t)a.H * xrow <= 40 * 1024) G = a.H;
   else { G = (int)(16384 / xrow); if (G < 1) G = 1; if (G > a.H) G = a.H; }
@@ -119,10 +119,10 @@ template <typename T, int ACT, int MODE>
 int launch_tma_sweep(const MrlaLightArgs& a, cudaStream_t st, const TmaPlan& p, const void* xptr, int64_t bs_x,
                      const void* optr, int64_t bs_o, const void* dyptr, int64_t bs_dy, float* mom) {
   CUtensorMap tx, to, tdy;
-  if (make_nhwc_tmap(&tx, xptr, a.dtype, a.B, a.C, a.H, a.W, bs_x, p.CB, a.W + 2, p.G)) return MRLA_ERR_UNSUPPORTED;
-  if (make_nhwc_tmap(&to, optr, a.dtype, a.B, a.C, a.H, a.W, bs_o, p.CB, a.W, p.G)) return MRLA_ERR_UNSUPPORTED;
+  if (make_nhwc_tmap(&tx, xptr, a.dtype, a.B, a.C, a.H, a.W, bs_x, p.CB, p.NQ * kCols + 2, p.G)) return MRLA_ERR_UNSUPPORTED;
+  if (make_nhwc_tmap(&to, optr, a.dtype, a.B, a.C, a.H, a.W, bs_o, p.CB, p.NQ * kCols, p.G)) return MRLA_ERR_UNSUPPORTED;
   tdy = to;
-  if (MODE == 2 && make_nhwc_tmap(&tdy, dyptr, a.dtype, a.B, a.C, a.H, a.W, bs_dy, p.CB, a.W, p.G))
+  if (MODE == 2 && make_nhwc_tmap(&tdy, dyptr, a.dtype, a.B, a.C, a.H, a.W, bs_dy, p.CB, p.NQ * kCols, p.G))
     return MRLA_ERR_UNSUPPORTED;
   TmaSweepParams P;
   P.B = a.B; P.C = a.C; P.H = a.H; P.W = a.W;
@@ -167,7 +167,7 @@ inline bool make_tma_bwd_plan(const MrlaLightArgs& a, TmaBwdPlan* p) {
   if (CB == 0) CB = 64;
   if (NQ * CB / 2 > 224) return false;
   if (a.act == MRLA_ACT_GELU && CB == 256) CB = 128;
-  const uint32_t xrow = (uint32_t)(WT + 4) * CB * es, trow = (uint32_t)(WT + 2) * CB * es;
+  const uint32_t xrow = (uint32_t)(NQ * kCols + 4) * CB * es, trow = (uint32_t)(NQ * kCols + 2) * CB * es;
   const uint32_t rowtot = xrow + 2 * trow;
   int G;
   if ((size_t)a.H * rowtot <= 48 * 1024) G = a.H;
@@ -196,9 +196,9 @@ inline bool make_tma_bwd_plan(const MrlaLightArgs& a, TmaBwdPlan* p) {
 template <typename T, int ACT>
 int launch_tma_bwd(const MrlaLightArgs& a, cudaStream_t st, const TmaBwdPlan& p, float* wv_part) {
   CUtensorMap tx, tdy, to;
-  if (make_nhwc_tmap(&tx, a.x, a.dtype, a.B, a.C, a.H, a.W, a.bs_x, p.CB, p.WT + 4, p.G)) return MRLA_ERR_UNSUPPORTED;
-  if (make_nhwc_tmap(&tdy, a.dy, a.dtype, a.B, a.C, a.H, a.W, a.bs_dy, p.CB, p.WT + 2, p.G)) return MRLA_ERR_UNSUPPORTED;
-  if (make_nhwc_tmap(&to, a.o, a.dtype, a.B, a.C, a.H, a.W, a.bs_o, p.CB, p.WT + 2, p.G)) return MRLA_ERR_UNSUPPORTED;
+  if (make_nhwc_tmap(&tx, a.x, a.dtype, a.B, a.C, a.H, a.W, a.bs_x, p.CB, p.NQ * kCols + 4, p.G)) return MRLA_ERR_UNSUPPORTED;
+  if (make_nhwc_tmap(&tdy, a.dy, a.dtype, a.B, a.C, a.H, a.W, a.bs_dy, p.CB, p.NQ * kCols + 2, p.G)) return MRLA_ERR_UNSUPPORTED;
+  if (make_nhwc_tmap(&to, a.o, a.dtype, a.B, a.C, a.H, a.W, a.bs_o, p.CB, p.NQ * kCols + 2, p.G)) return MRLA_ERR_UNSUPPORTED;
   cudaError_t e = cudaMemsetAsync(wv_part, 0, (size_t)p.maxslots * a.C * 9 * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
   TmaBwdParams P;

@@ -142,25 +142,16 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   const int lane = threadIdx.x & 31;
   constexpr int ES = sizeof(T);
   const uint32_t stages_s = smem_u32(stages);
-  const uint32_t xrow_bytes = (uint32_t)(P.W + 2) * CB * ES;
-  const uint32_t orow_bytes = (uint32_t)P.W * CB * ES;
-  // shared-memory byte offsets of this thread's window / output columns inside a tile row
-  uint32_t xoff[kWin], ooff[kCols];
-  float2 cmask[kCols];
+  // Tile rows are 4*NQ (+2 halo) columns wide: columns past the image are zero-filled by TMA, so every
+  // thread reads its window at compile-time offsets from one per-thread base (no clamping, no o/dy masks).
+  constexpr uint32_t CS = CB * ES;                      // bytes between adjacent columns
+  const uint32_t xrow_bytes = (uint32_t)(P.NQ * kCols + 2) * CS;
+  const uint32_t orow_bytes = (uint32_t)(P.NQ * kCols) * CS;
+  const uint32_t tbase = (uint32_t)(q * kCols) * CS + (uint32_t)p * 2 * ES;
+  const bool ragged = (P.W % kCols) != 0;               // last column group is partial
   bool cvalid[kCols];
 #pragma unroll
-  for (int j = 0; j < kWin; ++j) {
-    int sc = q * kCols + j;  // smem column index = image column + 1
-    if (sc > P.W + 1) sc = P.W + 1;
-    xoff[j] = (uint32_t)sc * CB * ES + (uint32_t)p * 2 * ES;
-  }
-#pragma unroll
-  for (int j = 0; j < kCols; ++j) {
-    const int col = q * kCols + j;
-    cvalid[j] = col < P.W;
-    cmask[j] = cvalid[j] ? f2(1.f, 1.f) : f2(0.f, 0.f);
-    ooff[j] = (uint32_t)(cvalid[j] ? col : P.W - 1) * CB * ES + (uint32_t)p * 2 * ES;
-  }
+  for (int j = 0; j < kCols; ++j) cvalid[j] = (q * kCols + j) < P.W;
 
   int st_cur = 0;        // stage of the group that holds x row r
   uint32_t ph_cur = 0;
@@ -186,7 +177,9 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     float2 acc[NACC > 0 ? NACC : 1];
 #pragma unroll
     for (int i = 0; i < (NACC > 0 ? NACC : 1); ++i) acc[i] = f2(0.f, 0.f);
-    T* yb = (MODE == 1) ? static_cast<T*>(P.y) + (int64_t)b * P.bs_y + c : nullptr;
+    // running pointer to this thread's first output column of the row being produced
+    T* yrow = (MODE == 1) ? static_cast<T*>(P.y) + (int64_t)b * P.bs_y + (int64_t)(q * kCols) * P.C + c : nullptr;
+    const int64_t y_row_stride = (int64_t)P.W * P.C;
 
     float2 win[3][kWin];
 #pragma unroll
@@ -202,9 +195,9 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           // ---- fetch x row r into window slot i ----
           if (r < P.H) {
             if (rr == 0) mbar_wait(&full[st_cur], ph_cur);
-            const uint32_t rowb = stages_s + (uint32_t)st_cur * P.stage_bytes + (uint32_t)rr * xrow_bytes;
+            const uint32_t rowb = stages_s + (uint32_t)st_cur * P.stage_bytes + (uint32_t)rr * xrow_bytes + tbase;
 #pragma unroll
-            for (int j = 0; j < kWin; ++j) win[i][j] = lds_pair<T>(rowb + xoff[j]);
+            for (int j = 0; j < kWin; ++j) win[i][j] = lds_pair<T>(rowb + j * CS);
           } else {
 #pragma unroll
             for (int j = 0; j < kWin; ++j) win[i][j] = f2(0.f, 0.f);
@@ -216,7 +209,7 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             const int sto = (rr == 0) ? st_prev : st_cur;
             const int rro_fix = (r == P.H) ? ((P.H - 1) % P.G) : rro;  // last image row may sit in a short group
             const int sto_fix = (r == P.H) ? st_prev : sto;
-            const uint32_t ob = stages_s + (uint32_t)sto_fix * P.stage_bytes + P.x_bytes + (uint32_t)rro_fix * orow_bytes;
+            const uint32_t ob = stages_s + (uint32_t)sto_fix * P.stage_bytes + P.x_bytes + (uint32_t)rro_fix * orow_bytes + tbase;
             const float2(&top)[kWin] = win[(i + 1) % 3];
             const float2(&mid)[kWin] = win[(i + 2) % 3];
             const float2(&bot)[kWin] = win[i];
@@ -225,11 +218,11 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
               float2 u = conv9(top, mid, bot, w9, j);
               float2 v = act2<ACT>(u);
               float2 ov = f2(0.f, 0.f), gv = f2(0.f, 0.f);
-              if (HAS_O) ov = fmul2(lds_pair<T>(ob + ooff[j]), cmask[j]);
-              if (HAS_DY) gv = fmul2(lds_pair<T>(ob + (HAS_O ? P.o_bytes : 0) + ooff[j]), cmask[j]);
+              if (HAS_O) ov = lds_pair<T>(ob + j * CS);
+              if (HAS_DY) gv = lds_pair<T>(ob + (HAS_O ? P.o_bytes : 0) + j * CS);
               const float2 xc = mid[j + 1];
               if (MODE == 0) {
-                v = fmul2(v, cmask[j]);
+                if (ragged && !cvalid[j]) v = f2(0.f, 0.f);
                 acc[0] = fadd2(acc[0], xc);
                 acc[1] = fadd2(acc[1], v);
                 acc[2] = ffma2(v, v, acc[2]);
@@ -246,9 +239,10 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 float2 t = ffma2(cA, v, cD);
                 if (HAS_O) t = ffma2(cL, ov, t);
                 t = ffma2(res2, xc, t);
-                if (chan_ok && cvalid[j]) stg_pair<T>(yb + ((int64_t)ro * P.W + (q * kCols + j)) * P.C, t);
+                if (chan_ok && cvalid[j]) stg_pair<T>(yrow + j * P.C, t);
               }
             }
+            if (MODE == 1) yrow += y_row_stride;
             // release the group whose last row was just consumed
             if (rro_fix == P.G - 1 || ro == P.H - 1) {
               __syncwarp();
@@ -370,21 +364,11 @@ k_light_nhwc_tma_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   const int lane = threadIdx.x & 31;
   constexpr int ES = sizeof(T);
   const uint32_t stages_s = smem_u32(stages);
-  const uint32_t xrow_bytes = (uint32_t)(P.WT + 4) * CB * ES;
-  const uint32_t trow_bytes = (uint32_t)(P.WT + 2) * CB * ES;
-  uint32_t xoff[XW], toff[TW];
-#pragma unroll
-  for (int k = 0; k < XW; ++k) {
-    int sc = q * kCols + k;
-    if (sc > P.WT + 3) sc = P.WT + 3;
-    xoff[k] = (uint32_t)sc * CB * ES + (uint32_t)p * 2 * ES;
-  }
-#pragma unroll
-  for (int j = 0; j < TW; ++j) {
-    int sc = q * kCols + j;
-    if (sc > P.WT + 1) sc = P.WT + 1;
-    toff[j] = (uint32_t)sc * CB * ES + (uint32_t)p * 2 * ES;
-  }
+  // tile rows are 4*NQ+4 (x) / 4*NQ+2 (dy, o) columns wide; columns outside the image are TMA zero fill
+  constexpr uint32_t CS = CB * ES;
+  const uint32_t xrow_bytes = (uint32_t)(P.NQ * kCols + 4) * CS;
+  const uint32_t trow_bytes = (uint32_t)(P.NQ * kCols + 2) * CS;
+  const uint32_t tbase = (uint32_t)(q * kCols) * CS + (uint32_t)p * 2 * ES;
 
   int st_cur = 0, st_prev = 0;
   uint32_t ph_cur = 0;
@@ -458,9 +442,10 @@ k_light_nhwc_tma_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     }
 #pragma unroll
     for (int j = 0; j < kCols; ++j) ovalid[j] = chan_ok && (q * kCols + j < wt);
-    T* dxb = static_cast<T*>(P.dx) + (int64_t)b * P.bs_dx + (int64_t)(w0 + q * kCols) * P.C + c;
-    T* dob = static_cast<T*>(P.dout) + (int64_t)b * P.bs_do + (int64_t)(w0 + q * kCols) * P.C + c;
     const int64_t row_stride = (int64_t)P.W * P.C;
+    // running row pointers: dxp -> row t-1 (the dX row emitted in a step), dop -> row t
+    T* dxp = static_cast<T*>(P.dx) + (int64_t)b * P.bs_dx + (int64_t)(w0 + q * kCols) * P.C + c - row_stride;
+    T* dop = static_cast<T*>(P.dout) + (int64_t)b * P.bs_do + (int64_t)(w0 + q * kCols) * P.C + c;
 
     float2 xw[3][XW];
     float2 da[3][kCols];   // rotating dX row accumulators: row t lives in slot t % 3
@@ -480,9 +465,9 @@ k_light_nhwc_tma_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         if (r <= P.H) {
           if (r < P.H) {
             if (rr == 0) mbar_wait(&full[st_cur], ph_cur);
-            const uint32_t rowb = stages_s + (uint32_t)st_cur * P.stage_bytes + (uint32_t)rr * xrow_bytes;
+            const uint32_t rowb = stages_s + (uint32_t)st_cur * P.stage_bytes + (uint32_t)rr * xrow_bytes + tbase;
 #pragma unroll
-            for (int k = 0; k < XW; ++k) xw[i][k] = lds_pair<T>(rowb + xoff[k]);
+            for (int k = 0; k < XW; ++k) xw[i][k] = lds_pair<T>(rowb + k * CS);
           } else {
 #pragma unroll
             for (int k = 0; k < XW; ++k) xw[i][k] = f2(0.f, 0.f);
@@ -491,7 +476,7 @@ k_light_nhwc_tma_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             const int t = r - 1;                                     // T row produced in this step
             const int rro = (r == P.H) ? ((P.H - 1) % P.G) : ((rr == 0) ? (P.G - 1) : rr - 1);
             const int sto = (r == P.H || rr == 0) ? st_prev : st_cur;
-            const uint32_t tb = stages_s + (uint32_t)sto * P.stage_bytes + P.x_bytes + (uint32_t)rro * trow_bytes;
+            const uint32_t tb = stages_s + (uint32_t)sto * P.stage_bytes + P.x_bytes + (uint32_t)rro * trow_bytes + tbase;
             const float2(&top)[XW] = xw[(i + 1) % 3];
             const float2(&mid)[XW] = xw[(i + 2) % 3];
             const float2(&bot)[XW] = xw[i];
@@ -509,8 +494,8 @@ k_light_nhwc_tma_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
               u = ffma2(w9[7], bot[j + 1], u);
               u = ffma2(w9[8], bot[j + 2], u);
               const float2 v = act2<ACT>(u);
-              const float2 gy = lds_pair<T>(tb + toff[j]);
-              const float2 ov = lds_pair<T>(tb + P.t_bytes + toff[j]);
+              const float2 gy = lds_pair<T>(tb + j * CS);
+              const float2 ov = lds_pair<T>(tb + P.t_bytes + j * CS);
               float2 ds = ffma2(q1, gy, q0);
               ds = ffma2(q2, v, ds);
               ds = ffma2(q3, ov, ds);
@@ -520,7 +505,7 @@ k_light_nhwc_tma_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
               if (j >= 1 && j <= kCols) {
                 const int jo = j - 1;
                 dyc_row[jo] = gy;
-                if (ovalid[jo]) stg_pair<T>(dob + (int64_t)t * row_stride + (int64_t)jo * P.C, fmul2(lm, ds));
+                if (ovalid[jo]) stg_pair<T>(dop + jo * P.C, fmul2(lm, ds));
                 // dWv[i][dj] += T[t][w] * x[t+i-1][w+dj-1]  (x window index = j + dj)
                 dw[0] = ffma2(tn[j], top[j], dw[0]);
                 dw[1] = ffma2(tn[j], top[j + 1], dw[1]);
@@ -554,16 +539,18 @@ k_light_nhwc_tma_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 #pragma unroll
               for (int jo = 0; jo < kCols; ++jo) {
                 const float2 out = fadd2(ffma2(res2, dyprev[jo], dyc), a_m1[jo]);
-                if (ovalid[jo]) stg_pair<T>(dxb + (int64_t)(t - 1) * row_stride + (int64_t)jo * P.C, out);
+                if (ovalid[jo]) stg_pair<T>(dxp + jo * P.C, out);
               }
             }
             if (t == P.H - 1) {
 #pragma unroll
               for (int jo = 0; jo < kCols; ++jo) {
                 const float2 out = fadd2(ffma2(res2, dyc_row[jo], dyc), a_0[jo]);
-                if (ovalid[jo]) stg_pair<T>(dxb + (int64_t)t * row_stride + (int64_t)jo * P.C, out);
+                if (ovalid[jo]) stg_pair<T>(dxp + row_stride + jo * P.C, out);
               }
             }
+            dxp += row_stride;
+            dop += row_stride;
 #pragma unroll
             for (int jo = 0; jo < kCols; ++jo) dyprev[jo] = dyc_row[jo];
             if (rro == P.G - 1 || t == P.H - 1) {
