@@ -125,6 +125,65 @@ int mrla_light_forward(const MrlaLightArgs* a, void* stream);
 /* dx, dout and all parameter gradients of the same expression. */
 int mrla_light_backward(const MrlaLightArgs* a, void* stream);
 
+
+/* One MRLA-base block tail at cache depth t (this block is the t-th of its stage, 1-based).
+ * The stage-scoped caches are caller-owned and written in place (no concatenation):
+ *   v / dv     : slot j (0-based) of sample b starts at  base + j*ts + b*bs  (elements, activation dtype)
+ *   kcache / dkcache : fp32 [B, t_cap, C]
+ * forward writes slot t-1 of v and row t-1 of kcache; backward adds p_j*dS into dv slots 0..t-1 and
+ * dlogit*q into dkcache rows 0..t-1 (accumulate=0: overwrite, used by the last block of the stage, whose
+ * backward runs first), then consumes dv slot t-1 / dkcache row t-1 as the total gradient of v_t / k_t. */
+typedef struct MrlaBaseArgs {
+  int32_t B, C, H, W;
+  int32_t dim_perhead, k_size, dtype, layout;
+  int32_t t, t_cap;
+  int32_t bn_mode;        /* MRLA_BN_* */
+  int32_t relu;           /* 1: ReLU after BN (resnet_mrla_base.py:126); 0: none (base22 / DeiT) */
+  int32_t residual, update_running;
+  int32_t accumulate;     /* backward only */
+  float eps, momentum;
+  int64_t bs_x, bs_y, bs_s, bs_dy, bs_dx;
+  int64_t bs_v, ts_v, bs_dv, ts_dv;
+  const void* x;          /* [B,C,H,W] */
+  void* v;                /* V cache base */
+  void* s;                /* [B,C,H,W] attention output S (saved for backward) */
+  void* y;                /* [B,C,H,W] */
+  float* kcache;          /* [B,t_cap,C] */
+  const float* wq;        /* [k] */
+  const float* wk;        /* [k] */
+  const float* wv;        /* [C,9] */
+  const float* gamma;     /* [C] or NULL */
+  const float* beta;      /* [C] or NULL */
+  float* running_mean;
+  float* running_var;
+  const float* drop_scale;/* [B] or NULL */
+  float* sx;              /* [B,C]   sum_hw x            (saved) */
+  float* q;               /* [B,C]   query               (saved) */
+  float* p;               /* [B,C/d,t] softmax weights   (saved) */
+  float* smom;            /* [2,B,C] sum S, sum S^2      (scratch) */
+  float* chan;            /* [4,C]   cA, cD, mean, rstd  (saved) */
+  const void* dy;         /* [B,C,H,W] */
+  void* dx;               /* [B,C,H,W] */
+  void* dv;               /* dV cache base */
+  float* dkcache;         /* [B,t_cap,C] */
+  float* dwq;
+  float* dwk;
+  float* dwv;
+  float* dgamma;
+  float* dbeta;
+  float* gmom;            /* [2,B,C] scratch */
+  float* dpm;             /* [t,B,C] scratch */
+  float* dyc;             /* [B,C]   scratch */
+  float* scratch;
+  size_t scratch_bytes;
+} MrlaBaseArgs;
+
+size_t mrla_sizeof_base_args(void);
+size_t mrla_base_bwd_scratch_bytes(const MrlaBaseArgs* a);
+/* y = residual*x + m_b * act( BN( sum_j softmax_j(q.K_j/sqrt(d)) V_j ) ), caches updated in place. */
+int mrla_base_forward(const MrlaBaseArgs* a, void* stream);
+int mrla_base_backward(const MrlaBaseArgs* a, void* stream);
+
 /* Number of kernel launches the last forward / backward call on this thread enqueued
  * (bench.py reports it as gpu_launches). */
 int mrla_last_launch_count(void);

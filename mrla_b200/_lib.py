@@ -43,12 +43,27 @@ class MrlaLightArgs(ctypes.Structure):
     )
 
 
+class MrlaBaseArgs(ctypes.Structure):
+    """Mirror of `struct MrlaBaseArgs` (include/mrla_b200.h) — field order must match."""
+    _fields_ = (
+        [(n, _i32) for n in ("B", "C", "H", "W", "dim_perhead", "k_size", "dtype", "layout", "t", "t_cap", "bn_mode",
+                             "relu", "residual", "update_running", "accumulate")]
+        + [("eps", _f32), ("momentum", _f32)]
+        + [(n, _i64) for n in ("bs_x", "bs_y", "bs_s", "bs_dy", "bs_dx", "bs_v", "ts_v", "bs_dv", "ts_dv")]
+        + [(n, _vp) for n in ("x", "v", "s", "y", "kcache", "wq", "wk", "wv", "gamma", "beta", "running_mean",
+                              "running_var", "drop_scale", "sx", "q", "p", "smom", "chan", "dy", "dx", "dv", "dkcache",
+                              "dwq", "dwk", "dwv", "dgamma", "dbeta", "gmom", "dpm", "dyc", "scratch")]
+        + [("scratch_bytes", ctypes.c_size_t)]
+    )
+
+
 _lib = None
 _lock = threading.Lock()
 
 EXPORTS = (
     "mrla_abi_version", "mrla_build_info", "mrla_last_launch_count", "mrla_sizeof_light_args",
     "mrla_light_bwd_scratch_bytes", "mrla_light_forward", "mrla_light_backward",
+    "mrla_sizeof_base_args", "mrla_base_bwd_scratch_bytes", "mrla_base_forward", "mrla_base_backward",
 )
 
 
@@ -74,7 +89,10 @@ def lib() -> ctypes.CDLL:
         L.mrla_sizeof_light_args.restype = ctypes.c_size_t
         if L.mrla_sizeof_light_args() != ctypes.sizeof(MrlaLightArgs):
             raise RuntimeError("MrlaLightArgs layout mismatch between _lib.py and include/mrla_b200.h")
-        for name, st in (("light", MrlaLightArgs),):
+        L.mrla_sizeof_base_args.restype = ctypes.c_size_t
+        if L.mrla_sizeof_base_args() != ctypes.sizeof(MrlaBaseArgs):
+            raise RuntimeError("MrlaBaseArgs layout mismatch between _lib.py and include/mrla_b200.h")
+        for name, st in (("light", MrlaLightArgs), ("base", MrlaBaseArgs)):
             f = getattr(L, f"mrla_{name}_bwd_scratch_bytes")
             f.restype = ctypes.c_size_t
             f.argtypes = [ctypes.POINTER(st)]

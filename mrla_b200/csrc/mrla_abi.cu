@@ -1,5 +1,5 @@
 // extern "C" entry points of libmrla_b200.so (see include/mrla_b200.h).
-#include "light_launch.cuh"
+#include "base_launch.cuh"
 
 namespace mrla {
 thread_local int g_launch_count = 0;
@@ -9,6 +9,13 @@ extern template int light_forward_t<__nv_bfloat16>(const MrlaLightArgs&, cudaStr
 extern template int light_backward_t<__nv_bfloat16>(const MrlaLightArgs&, cudaStream_t);
 extern template int light_forward_t<__half>(const MrlaLightArgs&, cudaStream_t);
 extern template int light_backward_t<__half>(const MrlaLightArgs&, cudaStream_t);
+
+extern template int base_forward_t<float>(const MrlaBaseArgs&, cudaStream_t);
+extern template int base_backward_t<float>(const MrlaBaseArgs&, cudaStream_t);
+extern template int base_forward_t<__nv_bfloat16>(const MrlaBaseArgs&, cudaStream_t);
+extern template int base_backward_t<__nv_bfloat16>(const MrlaBaseArgs&, cudaStream_t);
+extern template int base_forward_t<__half>(const MrlaBaseArgs&, cudaStream_t);
+extern template int base_backward_t<__half>(const MrlaBaseArgs&, cudaStream_t);
 
 static size_t esize(int dtype) { return dtype == MRLA_F32 ? 4 : 2; }
 
@@ -33,6 +40,31 @@ static int check_common(const MrlaLightArgs* a, bool bwd) {
     for (const void* p : ptrs)
       if (p && ((uintptr_t)p % al)) return MRLA_ERR_ALIGN;
     const int64_t bss[] = {a->bs_x, a->bs_o, a->bs_y, a->bs_dy, a->bs_dx, a->bs_do};
+    for (int64_t s : bss)
+      if (s % 4) return MRLA_ERR_ALIGN;
+  }
+  return MRLA_OK;
+}
+static int check_base(const MrlaBaseArgs* a, bool bwd) {
+  if (a == nullptr) return MRLA_ERR_NULL;
+  if (a->B < 1 || a->C < 1 || a->H < 1 || a->W < 1) return MRLA_ERR_SHAPE;
+  if (a->dim_perhead < 1 || a->C % a->dim_perhead) return MRLA_ERR_SHAPE;
+  if (a->k_size < 1 || a->k_size > 15 || a->k_size % 2 == 0) return MRLA_ERR_SHAPE;
+  if (a->t < 1 || a->t > a->t_cap) return MRLA_ERR_SHAPE;
+  if (a->dtype < MRLA_F32 || a->dtype > MRLA_F16) return MRLA_ERR_UNSUPPORTED;
+  if (a->layout != MRLA_NCHW && a->layout != MRLA_NHWC) return MRLA_ERR_UNSUPPORTED;
+  if (a->bn_mode < MRLA_BN_NONE || a->bn_mode > MRLA_BN_EVAL) return MRLA_ERR_UNSUPPORTED;
+  if (!a->x || !a->v || !a->s || !a->kcache || !a->wq || !a->wk || !a->wv || !a->sx || !a->q || !a->p || !a->chan)
+    return MRLA_ERR_NULL;
+  if (a->bn_mode != MRLA_BN_NONE && (!a->gamma || (!bwd && !a->beta))) return MRLA_ERR_NULL;
+  if (!bwd && a->bn_mode == MRLA_BN_EVAL && (!a->running_mean || !a->running_var)) return MRLA_ERR_NULL;
+  if (a->layout == MRLA_NHWC) {
+    const size_t al = 4 * esize(a->dtype);
+    if (a->C % 4) return MRLA_ERR_ALIGN;
+    const void* ptrs[] = {a->x, a->v, a->s, a->y, a->dy, a->dx, a->dv};
+    for (const void* p : ptrs)
+      if (p && ((uintptr_t)p % al)) return MRLA_ERR_ALIGN;
+    const int64_t bss[] = {a->bs_x, a->bs_y, a->bs_s, a->bs_dy, a->bs_dx, a->bs_v, a->ts_v, a->bs_dv, a->ts_dv};
     for (int64_t s : bss)
       if (s % 4) return MRLA_ERR_ALIGN;
   }
@@ -85,6 +117,39 @@ int mrla_light_backward(const MrlaLightArgs* a, void* stream) {
     case MRLA_F32: return light_backward_t<float>(*a, st);
     case MRLA_BF16: return light_backward_t<__nv_bfloat16>(*a, st);
     default: return light_backward_t<__half>(*a, st);
+  }
+}
+
+size_t mrla_sizeof_base_args(void) { return sizeof(MrlaBaseArgs); }
+
+size_t mrla_base_bwd_scratch_bytes(const MrlaBaseArgs* a) {
+  if (a == nullptr) return 0;
+  return base_bwd_scratch_floats(*a) * sizeof(float);
+}
+
+int mrla_base_forward(const MrlaBaseArgs* a, void* stream) {
+  g_launch_count = 0;
+  int rc = check_base(a, false);
+  if (rc) return rc;
+  if (!a->y || !a->smom) return MRLA_ERR_NULL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (a->dtype) {
+    case MRLA_F32: return base_forward_t<float>(*a, st);
+    case MRLA_BF16: return base_forward_t<__nv_bfloat16>(*a, st);
+    default: return base_forward_t<__half>(*a, st);
+  }
+}
+
+int mrla_base_backward(const MrlaBaseArgs* a, void* stream) {
+  g_launch_count = 0;
+  int rc = check_base(a, true);
+  if (rc) return rc;
+  if (!a->dy || !a->dx || !a->dv || !a->dkcache || !a->gmom || !a->dpm || !a->dyc || !a->scratch) return MRLA_ERR_NULL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (a->dtype) {
+    case MRLA_F32: return base_backward_t<float>(*a, st);
+    case MRLA_BF16: return base_backward_t<__nv_bfloat16>(*a, st);
+    default: return base_backward_t<__half>(*a, st);
   }
 }
 

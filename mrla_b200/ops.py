@@ -254,3 +254,219 @@ def light_tail(x: torch.Tensor, o: Optional[torch.Tensor], wq, wk, wv, lam=None,
     """Fused MRLA-light tail (see module docstring).  `x`/`o` are logical [B,C,H,W] tensors, either
     NCHW-contiguous or channels-last (any batch stride); the result has the layout of `x`."""
     return _LightTail.apply(x, o, wq, wk, wv, lam, gamma, beta, running_mean, running_var, drop_scale, cfg, out)
+
+
+# ===================================================================================== MRLA-base
+class BaseCfg(NamedTuple):
+    dim_perhead: int
+    k_size: int
+    bn_mode: int = _lib.BN_NONE
+    relu: bool = False
+    residual: bool = False
+    update_running: bool = True
+    eps: float = 1e-5
+    momentum: float = 0.1
+
+
+class StageCache:
+    """Stage-scoped K/V cache of MRLA-base, written IN PLACE.
+
+    The reference grows K [B,t,C] and V [B,t,C,H,W] with `torch.cat` in every block
+    (resnet/models/modules/mrla_base_module.py:65-70), re-copying the whole cache each time (O(T^2) traffic per
+    stage) and making autograd slice it back apart.  Here one buffer per stage holds the slots
+    (`v[j]` is a dense [B,C,H,W] activation in the layout of x, `k` is fp32 [B,T,C]); gradients w.r.t. the cached
+    slots are accumulated in place in `dv` / `dk` by the later blocks of the stage (their backward runs first
+    because the blocks are chained through the residual stream) and consumed by the block that produced the slot.
+    """
+
+    def __init__(self, like: torch.Tensor, layout: int, cap: int):
+        B, C, H, W = like.shape
+        self.shape, self.layout, self.dtype, self.device = (B, C, H, W), layout, like.dtype, like.device
+        self.cap = max(int(cap), 1)
+        self.t = 0
+        self.v = self._alloc_v(self.cap)
+        self.k = torch.empty((B, self.cap, C), dtype=torch.float32, device=like.device)
+        self.dv = None
+        self.dk = None
+        self.bwd_started = False
+        self.n_ext = 0  # slots that came from foreign prev_K / prev_V tensors
+
+    def _alloc_v(self, cap):
+        B, C, H, W = self.shape
+        shape = (cap, B, H, W, C) if self.layout == _lib.NHWC else (cap, B, C, H, W)
+        return torch.empty(shape, dtype=self.dtype, device=self.device)
+
+    def reserve(self, t: int):
+        if t <= self.cap:
+            return
+        cap = max(t, 2 * self.cap)
+        v = self._alloc_v(cap)
+        v[: self.cap].copy_(self.v)
+        k = torch.empty((self.shape[0], cap, self.shape[1]), dtype=torch.float32, device=self.device)
+        k[:, : self.cap].copy_(self.k)
+        self.v, self.k, self.cap = v, k, cap
+
+    def ensure_grads(self):
+        if self.dv is None:
+            self.dv = torch.empty_like(self.v)
+            self.dk = torch.empty_like(self.k)
+
+    # reference-shaped views ------------------------------------------------------------------
+    def K_view(self, t):
+        kv = self.k[:, :t]
+        return kv if self.dtype == torch.float32 else kv.to(self.dtype)
+
+    def V_view(self, t):
+        v = self.v[:t]
+        if self.layout == _lib.NHWC:
+            v = v.permute(0, 1, 4, 2, 3)  # [t,B,C,H,W]
+        return v.transpose(0, 1)         # [B,t,C,H,W]
+
+
+class _BaseTail(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, wq, wk, wv, gamma, beta, ext_k, ext_v, running_mean, running_var, drop_scale, cache, t,
+                cfg: BaseCfg, out):
+        _require_cuda(x, "x")
+        L = _lib.lib()
+        x_c, layout, bs_x = _canon(x, cache.layout)
+        B, C, H, W = x_c.shape
+        if out is not None:
+            lay = _layout_of(out)
+            if lay is None or lay[0] != layout or out.dtype != x.dtype or out.shape != x.shape:
+                raise RuntimeError("mrla_b200: `out` buffer must have the layout / dtype / shape of x")
+            y, bs_y = out, lay[1]
+        else:
+            y, bs_y = _empty_like_layout(x_c, layout), C * H * W
+        s = _empty_like_layout(x_c, layout)
+        g = C // cfg.dim_perhead
+        f32 = dict(dtype=torch.float32, device=x.device)
+        sxq = torch.empty((2, B, C), **f32)
+        p = torch.empty((B, g, t), **f32)
+        smom = torch.empty((2, B, C), **f32)
+        chan = torch.empty((4, C), **f32)
+        wq32, wk32, wv32, ga32, be32, ds32 = _f32(wq), _f32(wk), _f32(wv), _f32(gamma), _f32(beta), _f32(drop_scale)
+        rm = running_mean if (running_mean is None or running_mean.dtype == torch.float32) else running_mean.float()
+        rv = running_var if (running_var is None or running_var.dtype == torch.float32) else running_var.float()
+        N = C * H * W
+        a = _lib.MrlaBaseArgs()
+        a.B, a.C, a.H, a.W = B, C, H, W
+        a.dim_perhead, a.k_size, a.dtype, a.layout = cfg.dim_perhead, cfg.k_size, _DTYPES[x.dtype], layout
+        a.t, a.t_cap, a.bn_mode, a.relu = t, cache.cap, cfg.bn_mode, int(cfg.relu)
+        a.residual, a.update_running = int(cfg.residual), int(cfg.update_running and rm is not None)
+        a.eps, a.momentum = cfg.eps, cfg.momentum
+        a.bs_x, a.bs_y, a.bs_s = bs_x, bs_y, N
+        a.bs_v, a.ts_v = N, B * N
+        a.x, a.v, a.s, a.y, a.kcache = _ptr(x_c), _ptr(cache.v), _ptr(s), _ptr(y), _ptr(cache.k)
+        a.wq, a.wk, a.wv, a.gamma, a.beta = _ptr(wq32), _ptr(wk32), _ptr(wv32), _ptr(ga32), _ptr(be32)
+        a.running_mean, a.running_var, a.drop_scale = _ptr(rm), _ptr(rv), _ptr(ds32)
+        a.sx, a.q, a.p, a.smom, a.chan = _ptr(sxq[0]), _ptr(sxq[1]), _ptr(p), _ptr(smom), _ptr(chan)
+        ev = _Prof.begin()
+        _lib.check(L.mrla_base_forward(ctypes.byref(a), _stream()), "mrla_base_forward")
+        _Prof.end("base_fwd", (B, C, H, W, x.dtype, layout), ev)
+        launch_counter["fwd"] += L.mrla_last_launch_count()
+        if rm is not None and rm is not running_mean and cfg.bn_mode == _lib.BN_TRAIN and cfg.update_running:
+            running_mean.copy_(rm)
+            running_var.copy_(rv)
+        ctx.cfg, ctx.layout, ctx.cache, ctx.t, ctx.bs_x = cfg, layout, cache, t, bs_x
+        ctx.has_ext = ext_k is not None
+        ctx.param_meta = [(q_.shape, q_.dtype) if q_ is not None else None for q_ in (wq, wk, wv, gamma, beta)]
+        ctx.ext_meta = (ext_k.dtype, ext_v.dtype) if ctx.has_ext else None
+        ctx.save_for_backward(x_c, s, wq32, wk32, wv32, ga32, ds32, sxq, p, chan)
+        if out is not None:
+            ctx.mark_dirty(out)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _lib.lib()
+        x_c, s, wq32, wk32, wv32, ga32, ds32, sxq, p, chan = ctx.saved_tensors
+        cfg, layout, cache, t = ctx.cfg, ctx.layout, ctx.cache, ctx.t
+        B, C, H, W = x_c.shape
+        N = C * H * W
+        dy_c, _, bs_dy = _canon(dy, layout)
+        if dy_c.dtype != x_c.dtype:
+            dy_c = dy_c.to(x_c.dtype)
+        cache.ensure_grads()
+        dx = _empty_like_layout(x_c, layout)
+        f32 = dict(dtype=torch.float32, device=x_c.device)
+        k = cfg.k_size
+        dwqk = torch.empty((2, k), **f32)
+        dwv = torch.empty((C, 9), **f32)
+        dch = torch.empty((2, C), **f32)
+        gmom = torch.empty((2, B, C), **f32)
+        dpm = torch.empty((t, B, C), **f32)
+        dyc = torch.empty((B, C), **f32)
+        a = _lib.MrlaBaseArgs()
+        a.B, a.C, a.H, a.W = B, C, H, W
+        a.dim_perhead, a.k_size, a.dtype, a.layout = cfg.dim_perhead, cfg.k_size, _DTYPES[x_c.dtype], layout
+        a.t, a.t_cap, a.bn_mode, a.relu = t, cache.cap, cfg.bn_mode, int(cfg.relu)
+        a.residual, a.update_running, a.accumulate = int(cfg.residual), 0, int(cache.bwd_started)
+        a.eps, a.momentum = cfg.eps, cfg.momentum
+        a.bs_x, a.bs_s, a.bs_dy, a.bs_dx = ctx.bs_x, N, bs_dy, N
+        a.bs_v, a.ts_v, a.bs_dv, a.ts_dv = N, B * N, N, B * N
+        a.x, a.v, a.s, a.kcache = _ptr(x_c), _ptr(cache.v), _ptr(s), _ptr(cache.k)
+        a.wq, a.wk, a.wv, a.gamma, a.drop_scale = _ptr(wq32), _ptr(wk32), _ptr(wv32), _ptr(ga32), _ptr(ds32)
+        a.sx, a.q, a.p, a.chan = _ptr(sxq[0]), _ptr(sxq[1]), _ptr(p), _ptr(chan)
+        a.dy, a.dx, a.dv, a.dkcache = _ptr(dy_c), _ptr(dx), _ptr(cache.dv), _ptr(cache.dk)
+        a.dwq, a.dwk, a.dwv = _ptr(dwqk[0]), _ptr(dwqk[1]), _ptr(dwv)
+        has_bn = cfg.bn_mode != _lib.BN_NONE
+        a.dgamma = _ptr(dch[0]) if has_bn else None
+        a.dbeta = _ptr(dch[1]) if has_bn else None
+        a.gmom, a.dpm, a.dyc = _ptr(gmom), _ptr(dpm), _ptr(dyc)
+        nbytes = L.mrla_base_bwd_scratch_bytes(ctypes.byref(a))
+        scratch = torch.empty((max(nbytes, 4) + 3) // 4, **f32)
+        a.scratch, a.scratch_bytes = _ptr(scratch), scratch.numel() * 4
+        ev = _Prof.begin()
+        _lib.check(L.mrla_base_backward(ctypes.byref(a), _stream()), "mrla_base_backward")
+        _Prof.end("base_bwd", (B, C, H, W, x_c.dtype, layout), ev)
+        launch_counter["bwd"] += L.mrla_last_launch_count()
+        cache.bwd_started = True
+
+        def back(i, g_):
+            meta = ctx.param_meta[i]
+            return None if meta is None or g_ is None else g_.reshape(meta[0]).to(meta[1])
+
+        dk_ext = dv_ext = None
+        if ctx.has_ext:
+            n = cache.n_ext
+            dk_ext = cache.dk[:, :n].to(ctx.ext_meta[0])
+            dvx = cache.dv[:n]
+            if layout == _lib.NHWC:
+                dvx = dvx.permute(0, 1, 4, 2, 3)
+            dv_ext = dvx.transpose(0, 1).to(ctx.ext_meta[1])
+        return (dx, back(0, dwqk[0]), back(1, dwqk[1]), back(2, dwv), back(3, dch[0]) if has_bn else None,
+                back(4, dch[1]) if has_bn else None, dk_ext, dv_ext, None, None, None, None, None, None, None)
+
+
+def base_tail(x, prev_k, prev_v, wq, wk, wv, gamma=None, beta=None, running_mean=None, running_var=None,
+              drop_scale=None, *, init_cell: bool, cfg: BaseCfg, cap_hint: int = 8, out=None):
+    """Fused MRLA-base tail.  Returns (y, K, V) with K [B,t,C] / V [B,t,C,H,W] views of the in-place stage cache
+    (reference signature: mrla_base_module.py:54-89 `forward(x, prev_K, prev_V) -> (out, K, V)`)."""
+    _require_cuda(x, "x")
+    x_c, layout, _ = _canon(x)
+    ext_k = ext_v = None
+    if init_cell or prev_k is None:
+        cache = StageCache(x_c, layout, cap_hint)
+    else:
+        cache = getattr(prev_k, "_mrla_cache", None)
+        if cache is None or cache.shape != tuple(x_c.shape) or cache.dtype != x_c.dtype or cache.layout != layout:
+            # foreign tensors (not produced by this op): import them into a fresh cache; their gradients are
+            # returned through the autograd edge of this call
+            n = prev_k.shape[1]
+            cache = StageCache(x_c, layout, max(cap_hint, n + 1))
+            cache.k[:, :n].copy_(prev_k.detach().float())
+            pv = prev_v.detach().transpose(0, 1)  # [n,B,C,H,W]
+            if layout == _lib.NHWC:
+                pv = pv.permute(0, 1, 3, 4, 2)
+            cache.v[:n].copy_(pv)
+            cache.t = cache.n_ext = n
+            ext_k, ext_v = prev_k, prev_v
+    t = cache.t + 1
+    cache.reserve(t)
+    y = _BaseTail.apply(x_c, wq, wk, wv, gamma, beta, ext_k, ext_v, running_mean, running_var, drop_scale, cache, t,
+                        cfg, out)
+    cache.t = t
+    K, V = cache.K_view(t), cache.V_view(t)
+    K._mrla_cache = cache
+    return y, K, V

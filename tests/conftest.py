@@ -38,6 +38,15 @@ def rel_err(a, b):
     return (a - b).abs().max().item() / denom
 
 
+def rel_err_l2(a, b):
+    """||a-b||_2 / ||b||_2 — used for bf16 paths gated by a ReLU, where a sign flip of a near-zero
+    pre-activation (pure rounding) moves single elements by O(1) and makes the max-norm meaningless."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    denom = b.norm().item()
+    return (a - b).norm().item() / (denom if denom > 0 else 1.0)
+
+
 @pytest.fixture(scope="session")
 def cuda_device():
     if not torch.cuda.is_available():
