@@ -325,8 +325,8 @@ class StageCache:
 
 class _BaseTail(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, wq, wk, wv, gamma, beta, ext_k, ext_v, running_mean, running_var, drop_scale, cache, t,
-                cfg: BaseCfg, out):
+    def forward(ctx, x, wq, wk, wv, gamma, beta, ext_k, ext_v, token, running_mean, running_var, drop_scale, cache,
+                t, cfg: BaseCfg, out):
         _require_cuda(x, "x")
         L = _lib.lib()
         x_c, layout, bs_x = _canon(x, cache.layout)
@@ -373,12 +373,16 @@ class _BaseTail(torch.autograd.Function):
         ctx.param_meta = [(q_.shape, q_.dtype) if q_ is not None else None for q_ in (wq, wk, wv, gamma, beta)]
         ctx.ext_meta = (ext_k.dtype, ext_v.dtype) if ctx.has_ext else None
         ctx.save_for_backward(x_c, s, wq32, wk32, wv32, ga32, ds32, sxq, p, chan)
+        ctx.has_token = token is not None
         if out is not None:
             ctx.mark_dirty(out)
-        return y
+        # `token` chains the blocks of a stage in the autograd graph (block t consumes the token block t-1
+        # emitted), so the backward of block t is guaranteed to run before that of block t-1 even when the
+        # activations themselves are not chained — the in-place dV / dK accumulation relies on that order.
+        return y, torch.zeros((), dtype=torch.float32, device=x.device)
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dtoken):
         L = _lib.lib()
         x_c, s, wq32, wk32, wv32, ga32, ds32, sxq, p, chan = ctx.saved_tensors
         cfg, layout, cache, t = ctx.cfg, ctx.layout, ctx.cache, ctx.t
@@ -435,8 +439,9 @@ class _BaseTail(torch.autograd.Function):
             if layout == _lib.NHWC:
                 dvx = dvx.permute(0, 1, 4, 2, 3)
             dv_ext = dvx.transpose(0, 1).to(ctx.ext_meta[1])
+        dtok = torch.zeros((), dtype=torch.float32, device=x_c.device) if ctx.has_token else None
         return (dx, back(0, dwqk[0]), back(1, dwqk[1]), back(2, dwv), back(3, dch[0]) if has_bn else None,
-                back(4, dch[1]) if has_bn else None, dk_ext, dv_ext, None, None, None, None, None, None, None)
+                back(4, dch[1]) if has_bn else None, dk_ext, dv_ext, dtok, None, None, None, None, None, None, None)
 
 
 def base_tail(x, prev_k, prev_v, wq, wk, wv, gamma=None, beta=None, running_mean=None, running_var=None,
@@ -464,8 +469,9 @@ def base_tail(x, prev_k, prev_v, wq, wk, wv, gamma=None, beta=None, running_mean
             ext_k, ext_v = prev_k, prev_v
     t = cache.t + 1
     cache.reserve(t)
-    y = _BaseTail.apply(x_c, wq, wk, wv, gamma, beta, ext_k, ext_v, running_mean, running_var, drop_scale, cache, t,
-                        cfg, out)
+    y, token = _BaseTail.apply(x_c, wq, wk, wv, gamma, beta, ext_k, ext_v, getattr(cache, "token", None),
+                               running_mean, running_var, drop_scale, cache, t, cfg, out)
+    cache.token = token if token.requires_grad else None
     cache.t = t
     K, V = cache.K_view(t), cache.V_view(t)
     K._mrla_cache = cache
