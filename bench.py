@@ -88,10 +88,11 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ reference arm
-def cpu_reference_run(steps: int, warmup: int, batch: int = 32):
+def cpu_reference_run(steps: int, warmup: int, batch: int = 0):
     """The reference's CPU path (oracle port of resnet50_mrlal; /root/reference is absent on the GPU box):
     fwd+bwd of BASELINE.json configs[0] (batch 32 x 3 x 224 x 224 fp32) on all host cores."""
     from oracle.resnet_oracle import resnet50_mrlal_oracle
+    batch = batch or int(os.environ.get("MRLA_BENCH_CPU_BATCH", "32"))  # env override: CPU test-suite only
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)

@@ -1,0 +1,92 @@
+"""CPU-only checks of the C-ABI boundary: the library loads, exports every function include/mrla_b200.h declares,
+the ctypes struct mirrors match the compiled layout, and argument validation returns the documented negative codes
+BEFORE any CUDA work is enqueued (so these calls are safe without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from mrla_b200 import _lib
+
+HEADER = os.path.join(ROOT, "include", "mrla_b200.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mrla_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_loads_and_reports_build():
+    L = _lib.lib()
+    assert L.mrla_abi_version() == _lib.ABI_VERSION
+    assert b"sm_100a" in L.mrla_build_info()
+
+
+def test_every_declared_symbol_is_exported():
+    L = _lib.lib()
+    names = _declared_functions()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/mrla_b200.h but not exported"
+    assert set(_lib.EXPORTS) <= set(names)
+
+
+def test_struct_mirrors_match():
+    L = _lib.lib()
+    assert L.mrla_sizeof_light_args() == ctypes.sizeof(_lib.MrlaLightArgs)
+    assert L.mrla_sizeof_base_args() == ctypes.sizeof(_lib.MrlaBaseArgs)
+
+
+def _light_args(**kw):
+    a = _lib.MrlaLightArgs()
+    a.B, a.C, a.H, a.W, a.dim_perhead, a.k_size = 2, 64, 7, 7, 32, 3
+    a.dtype, a.layout, a.bn_mode = _lib.F32, _lib.NCHW, _lib.BN_NONE
+    fake = 0x1000  # never dereferenced: validation fails first
+    for f in ("x", "y", "wq", "wk", "wv", "mom", "gate", "mean", "rstd", "coef"):
+        setattr(a, f, fake)
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
+
+
+@pytest.mark.parametrize("kw,code", [
+    (dict(B=0), -2), (dict(dim_perhead=48), -2), (dict(k_size=4), -2), (dict(k_size=17), -2),
+    (dict(x=None), -1), (dict(wv=None), -1), (dict(o=0x1000, lam=None), -1),
+    (dict(bn_mode=_lib.BN_TRAIN, gamma=None), -1), (dict(dtype=7), -4), (dict(layout=5), -4), (dict(act=3), -4),
+    (dict(layout=_lib.NHWC, C=66, dim_perhead=33), -3), (dict(layout=_lib.NHWC, x=0x1002), -3),
+    (dict(layout=_lib.NHWC, bs_x=6), -3),
+])
+def test_light_argument_validation(kw, code):
+    L = _lib.lib()
+    a = _light_args(**kw)
+    assert L.mrla_light_forward(ctypes.byref(a), None) == code
+
+
+def test_backward_validation_and_scratch_size():
+    L = _lib.lib()
+    a = _light_args()
+    assert L.mrla_light_backward(ctypes.byref(a), None) == -1  # dy/dx/gmom/bcoef/scratch missing
+    assert L.mrla_light_bwd_scratch_bytes(ctypes.byref(a)) > 0
+    assert L.mrla_light_forward(None, None) == -1
+
+
+def test_base_argument_validation():
+    L = _lib.lib()
+    a = _lib.MrlaBaseArgs()
+    assert L.mrla_base_forward(ctypes.byref(a), None) == -2
+    a.B, a.C, a.H, a.W, a.dim_perhead, a.k_size, a.t, a.t_cap = 2, 64, 7, 7, 16, 3, 3, 2
+    assert L.mrla_base_forward(ctypes.byref(a), None) == -2  # t > t_cap
+    a.t_cap = 4
+    assert L.mrla_base_forward(ctypes.byref(a), None) == -1  # NULL tensors
+    assert L.mrla_base_backward(None, None) == -1
+
+
+def test_check_error_messages():
+    with pytest.raises(RuntimeError, match="MRLA_ERR_ALIGN"):
+        _lib.check(-3, "x")
+    with pytest.raises(RuntimeError, match="CUDA error 700"):
+        _lib.check(700, "x")
+    _lib.check(0, "x")
