@@ -72,7 +72,7 @@ inline MidShape mid_shape(const MrlaLightArgs& a, bool full) {
 
 // ------------------------------------------------------------------------------------ v2 (TMA) planning
 struct TmaPlan {
-  int CB, NQ, G, S, ncb, items, cons_threads, grid;
+  int CB, NQ, G, S, ncb, items, cons_threads, grid, big;
   uint32_t x_bytes, o_bytes, stage_bytes;
   size_t smem;
 };
@@ -90,23 +90,27 @@ inline bool make_tma_plan(const MrlaLightArgs& a, int ntiles, int nacc, TmaPlan*
   }
   if (a.act == MRLA_ACT_GELU && CB == 256) CB = 128;
   const uint32_t xrow = (uint32_t)(NQ * kCols + 2) * CB * es, orow = (uint32_t)(NQ * kCols) * CB * es;
-  int G;
-  if ((size_t)a.H * xrow <= 40 * 1024) G = a.H;
-  else { G = (int)(16384 / xrow); if (G < 1) G = 1; if (G > a.H) G = a.H; }
+  p->cons_threads = NQ * (CB / 2);
+  p->big = p->cons_threads > 256;
+  const size_t budget = (p->big ? 200 : 100) * 1024;   // !big: two CTAs share one SM
+  // rows per TMA group: about a fifth of the ring per stage (>= 4 stages in flight)
+  const uint32_t rowtot = xrow + (uint32_t)ntiles * orow;
+  int G = (int)((budget / 5) / rowtot);
+  if (G < 1) G = 1;
+  if (G > a.H) G = a.H;
   p->CB = CB; p->NQ = NQ; p->G = G;
   p->x_bytes = (uint32_t)G * xrow;
   p->o_bytes = (uint32_t)G * orow;
   p->stage_bytes = p->x_bytes + (uint32_t)ntiles * p->o_bytes;
   const size_t red = (size_t)NQ * nacc * (CB / 2) * sizeof(float2);
-  const size_t budget = 200 * 1024;
   int S = (int)((budget - red) / p->stage_bytes);
   if (S > 8) S = 8;
   if (S < 2) return false;
   p->S = S;
   p->ncb = (a.C + CB - 1) / CB;
   p->items = a.B * p->ncb;
-  p->cons_threads = NQ * (CB / 2);
-  p->grid = p->items < kNumSMs ? p->items : kNumSMs;
+  const int slots = p->big ? kNumSMs : 2 * kNumSMs;
+  p->grid = p->items < slots ? p->items : slots;
   p->smem = 256 + (size_t)S * p->stage_bytes + red;
   return true;
 }
@@ -130,12 +134,16 @@ int launch_tma_sweep(const MrlaLightArgs& a, cudaStream_t st, const TmaPlan& p, 
   P.x_bytes = p.x_bytes; P.o_bytes = p.o_bytes; P.stage_bytes = p.stage_bytes;
   P.wv = a.wv; P.mom = mom; P.coef = a.coef; P.y = a.y; P.bs_y = a.bs_y; P.res = a.residual ? 1.f : 0.f;
   const int threads = 32 + p.cons_threads;
-#define MRLA_TMA_LAUNCH(CBV)                                                                              \
+#define MRLA_TMA_LAUNCH1(CBV, BIGV)                                                                       \
   {                                                                                                       \
-    auto k = k_light_nhwc_tma<T, CBV, ACT, true, MODE>;                                                   \
+    auto k = k_light_nhwc_tma<T, CBV, ACT, true, MODE, BIGV>;                                             \
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);    \
     if (e != cudaSuccess) return (int)e;                                                                  \
     k<<<p.grid, threads, p.smem, st>>>(tx, to, tdy, P);                                                   \
+  }
+#define MRLA_TMA_LAUNCH(CBV)                                                                              \
+  {                                                                                                       \
+    if (p.big) MRLA_TMA_LAUNCH1(CBV, true) else MRLA_TMA_LAUNCH1(CBV, false)                              \
   }
   if (p.CB == 64) MRLA_TMA_LAUNCH(64)
   else if (p.CB == 128) MRLA_TMA_LAUNCH(128)
@@ -144,12 +152,13 @@ int launch_tma_sweep(const MrlaLightArgs& a, cudaStream_t st, const TmaPlan& p, 
     MRLA_TMA_LAUNCH(ACT == 1 ? 128 : 256)
   }
 #undef MRLA_TMA_LAUNCH
+#undef MRLA_TMA_LAUNCH1
   MRLA_CHECK_LAUNCH();
   return MRLA_OK;
 }
 
 struct TmaBwdPlan {
-  int CB, NQ, NT, WT, G, S, ncb, items, ipc, grid, cons_threads, maxslots;
+  int CB, NQ, NT, WT, G, S, ncb, items, ipc, grid, cons_threads, maxslots, big;
   uint32_t x_bytes, t_bytes, stage_bytes;
   size_t smem;
 };
@@ -169,21 +178,24 @@ inline bool make_tma_bwd_plan(const MrlaLightArgs& a, TmaBwdPlan* p) {
   if (a.act == MRLA_ACT_GELU && CB == 256) CB = 128;
   const uint32_t xrow = (uint32_t)(NQ * kCols + 4) * CB * es, trow = (uint32_t)(NQ * kCols + 2) * CB * es;
   const uint32_t rowtot = xrow + 2 * trow;
-  int G;
-  if ((size_t)a.H * rowtot <= 48 * 1024) G = a.H;
-  else { G = (int)(12288 / xrow); if (G < 1) G = 1; if (G > a.H) G = a.H; }
+  p->big = NQ * (CB / 2) > 128;
+  int G = (int)((((size_t)(p->big ? 200 : 100) * 1024) / 5) / rowtot);
+  if (G < 1) G = 1;
+  if (G > a.H) G = a.H;
   p->CB = CB; p->NQ = NQ; p->NT = NT; p->WT = WT; p->G = G;
   p->x_bytes = (uint32_t)G * xrow;
   p->t_bytes = (uint32_t)G * trow;
   p->stage_bytes = p->x_bytes + 2 * p->t_bytes;
   const size_t red = (size_t)NQ * 9 * (CB / 2) * sizeof(float2);
-  int S = (int)((200 * 1024 - red) / p->stage_bytes);
+  p->big = NQ * (CB / 2) > 128;
+  int S = (int)(((p->big ? 200 : 100) * 1024 - red) / p->stage_bytes);
   if (S > 8) S = 8;
   if (S < 2) return false;
   p->S = S;
   p->ncb = (a.C + CB - 1) / CB;
   p->items = p->ncb * a.B * NT;
-  int grid = p->items < kNumSMs ? p->items : kNumSMs;
+  const int slots = p->big ? kNumSMs : 2 * kNumSMs;
+  int grid = p->items < slots ? p->items : slots;
   p->ipc = (p->items + grid - 1) / grid;
   p->grid = (p->items + p->ipc - 1) / p->ipc;
   const int ipcb = a.B * NT;
@@ -209,12 +221,16 @@ int launch_tma_bwd(const MrlaLightArgs& a, cudaStream_t st, const TmaBwdPlan& p,
   P.wv = a.wv; P.lam = a.lam; P.bcoef = a.bcoef; P.dx = a.dx; P.dout = a.dout; P.bs_dx = a.bs_dx; P.bs_do = a.bs_do;
   P.res = a.residual ? 1.f : 0.f; P.wv_part = wv_part;
   const int threads = 32 + p.cons_threads;
-#define MRLA_TMA_LAUNCH(CBV)                                                                              \
+#define MRLA_TMA_LAUNCH1(CBV, BIGV)                                                                       \
   {                                                                                                       \
-    auto k = k_light_nhwc_tma_bwd<T, CBV, ACT>;                                                           \
+    auto k = k_light_nhwc_tma_bwd<T, CBV, ACT, BIGV>;                                                     \
     e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);                \
     if (e != cudaSuccess) return (int)e;                                                                  \
     k<<<p.grid, threads, p.smem, st>>>(tx, tdy, to, P);                                                   \
+  }
+#define MRLA_TMA_LAUNCH(CBV)                                                                              \
+  {                                                                                                       \
+    if (p.big) MRLA_TMA_LAUNCH1(CBV, true) else MRLA_TMA_LAUNCH1(CBV, false)                              \
   }
   if (p.CB == 64) MRLA_TMA_LAUNCH(64)
   else if (p.CB == 128) MRLA_TMA_LAUNCH(128)
@@ -223,6 +239,7 @@ int launch_tma_bwd(const MrlaLightArgs& a, cudaStream_t st, const TmaBwdPlan& p,
     MRLA_TMA_LAUNCH(ACT == 1 ? 128 : 256)
   }
 #undef MRLA_TMA_LAUNCH
+#undef MRLA_TMA_LAUNCH1
   MRLA_CHECK_LAUNCH();
   return MRLA_OK;
 }

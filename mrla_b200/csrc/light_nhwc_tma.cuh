@@ -85,10 +85,34 @@ __device__ __forceinline__ float2 conv9(const float2 (&top)[kWin], const float2 
   return s;
 }
 
+// all kCols outputs of one row, tap-major so the kCols FFMA2 chains are independent and interleaved
+__device__ __forceinline__ void conv9x4(const float2 (&top)[kWin], const float2 (&mid)[kWin], const float2 (&bot)[kWin],
+                                        const float2 (&w9)[9], float2 (&u)[kCols]) {
+#pragma unroll
+  for (int j = 0; j < kCols; ++j) u[j] = fmul2(w9[0], top[j]);
+#pragma unroll
+  for (int j = 0; j < kCols; ++j) u[j] = ffma2(w9[1], top[j + 1], u[j]);
+#pragma unroll
+  for (int j = 0; j < kCols; ++j) u[j] = ffma2(w9[2], top[j + 2], u[j]);
+#pragma unroll
+  for (int j = 0; j < kCols; ++j) u[j] = ffma2(w9[3], mid[j], u[j]);
+#pragma unroll
+  for (int j = 0; j < kCols; ++j) u[j] = ffma2(w9[4], mid[j + 1], u[j]);
+#pragma unroll
+  for (int j = 0; j < kCols; ++j) u[j] = ffma2(w9[5], mid[j + 2], u[j]);
+#pragma unroll
+  for (int j = 0; j < kCols; ++j) u[j] = ffma2(w9[6], bot[j], u[j]);
+#pragma unroll
+  for (int j = 0; j < kCols; ++j) u[j] = ffma2(w9[7], bot[j + 1], u[j]);
+#pragma unroll
+  for (int j = 0; j < kCols; ++j) u[j] = ffma2(w9[8], bot[j + 2], u[j]);
+}
+
 // ---------------------------------------------------------------------------- the kernel
 // MODE 0: forward moments (Σx ΣV ΣV² [ΣVo Σo Σo²]) ; MODE 1: forward apply (y) ; MODE 2: backward moments (Σdy ΣdyV [Σdyo])
-template <typename T, int CB, int ACT, bool HAS_O, int MODE>
-__global__ void __launch_bounds__(480, 1)
+// BIG: one 480-thread CTA per SM (W = 56 / 28); !BIG: <= 288 threads, two CTAs per SM (small images)
+template <typename T, int CB, int ACT, bool HAS_O, int MODE, bool BIG>
+__global__ void __launch_bounds__(BIG ? 480 : 288, BIG ? 1 : 2)
 k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_o,
                  const __grid_constant__ CUtensorMap tm_dy, TmaSweepParams P) {
   constexpr int NP = CB / 2;                                  // channel pairs per block
@@ -174,9 +198,9 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       cD = *reinterpret_cast<const float2*>(cp + 2 * BC);
     }
     const float2 res2 = f2(P.res, P.res);
-    float2 acc[NACC > 0 ? NACC : 1];
+    float2 acc[NACC > 0 ? NACC : 1], accb[NACC > 0 ? NACC : 1];  // even / odd columns: two independent chains
 #pragma unroll
-    for (int i = 0; i < (NACC > 0 ? NACC : 1); ++i) acc[i] = f2(0.f, 0.f);
+    for (int i = 0; i < (NACC > 0 ? NACC : 1); ++i) { acc[i] = f2(0.f, 0.f); accb[i] = f2(0.f, 0.f); }
     // running pointer to this thread's first output column of the row being produced
     T* yrow = (MODE == 1) ? static_cast<T*>(P.y) + (int64_t)b * P.bs_y + (int64_t)(q * kCols) * P.C + c : nullptr;
     const int64_t y_row_stride = (int64_t)P.W * P.C;
@@ -213,28 +237,30 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             const float2(&top)[kWin] = win[(i + 1) % 3];
             const float2(&mid)[kWin] = win[(i + 2) % 3];
             const float2(&bot)[kWin] = win[i];
+            float2 u4[kCols];
+            conv9x4(top, mid, bot, w9, u4);
 #pragma unroll
             for (int j = 0; j < kCols; ++j) {
-              float2 u = conv9(top, mid, bot, w9, j);
-              float2 v = act2<ACT>(u);
+              float2 v = act2<ACT>(u4[j]);
               float2 ov = f2(0.f, 0.f), gv = f2(0.f, 0.f);
               if (HAS_O) ov = lds_pair<T>(ob + j * CS);
               if (HAS_DY) gv = lds_pair<T>(ob + (HAS_O ? P.o_bytes : 0) + j * CS);
               const float2 xc = mid[j + 1];
+              float2(&A)[NACC > 0 ? NACC : 1] = (j & 1) ? accb : acc;
               if (MODE == 0) {
                 if (ragged && !cvalid[j]) v = f2(0.f, 0.f);
-                acc[0] = fadd2(acc[0], xc);
-                acc[1] = fadd2(acc[1], v);
-                acc[2] = ffma2(v, v, acc[2]);
+                A[0] = fadd2(A[0], xc);
+                A[1] = fadd2(A[1], v);
+                A[2] = ffma2(v, v, A[2]);
                 if (HAS_O) {
-                  acc[3] = ffma2(v, ov, acc[3]);
-                  acc[4] = fadd2(acc[4], ov);
-                  acc[5] = ffma2(ov, ov, acc[5]);
+                  A[3] = ffma2(v, ov, A[3]);
+                  A[4] = fadd2(A[4], ov);
+                  A[5] = ffma2(ov, ov, A[5]);
                 }
               } else if (MODE == 2) {
-                acc[0] = fadd2(acc[0], gv);
-                acc[1] = ffma2(gv, v, acc[1]);
-                if (HAS_O) acc[2] = ffma2(gv, ov, acc[2]);
+                A[0] = fadd2(A[0], gv);
+                A[1] = ffma2(gv, v, A[1]);
+                if (HAS_O) A[2] = ffma2(gv, ov, A[2]);
               } else {
                 float2 t = ffma2(cA, v, cD);
                 if (HAS_O) t = ffma2(cL, ov, t);
@@ -264,7 +290,7 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     if (NACC > 0) {
       // deterministic reduction over the NQ column groups of every channel pair
 #pragma unroll
-      for (int i = 0; i < NACC; ++i) red[((size_t)q * NACC + i) * NP + p] = acc[i];
+      for (int i = 0; i < NACC; ++i) red[((size_t)q * NACC + i) * NP + p] = fadd2(acc[i], accb[i]);
       named_bar_sync(1, P.cons_threads);
       const int64_t BC = (int64_t)P.B * P.C;
       for (int idx = ct; idx < NACC * NP; idx += P.cons_threads) {
@@ -307,8 +333,9 @@ struct TmaBwdParams {
   float* wv_part;      // [maxslots, C, 9]
 };
 
-template <typename T, int CB, int ACT>
-__global__ void __launch_bounds__(256, 1)
+// BIG: <= 256 threads, one CTA per SM; !BIG: <= 160 threads, two CTAs per SM (small images)
+template <typename T, int CB, int ACT, bool BIG>
+__global__ void __launch_bounds__(BIG ? 256 : 160, BIG ? 1 : 2)
 k_light_nhwc_tma_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy,
                      const __grid_constant__ CUtensorMap tm_o, TmaBwdParams P) {
   constexpr int NP = CB / 2;
