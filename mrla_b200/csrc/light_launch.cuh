@@ -244,6 +244,86 @@ int launch_tma_bwd(const MrlaLightArgs& a, cudaStream_t st, const TmaBwdPlan& p,
   return MRLA_OK;
 }
 
+// v3 sweep B (T ring): full-width rows, same tiles as sweep A
+inline bool make_tma_ring_plan(const MrlaLightArgs& a, TmaBwdPlan* p) {
+  if (a.layout != MRLA_NHWC || a.C % 8 || a.W > 56) return false;
+  const int es = a.dtype == MRLA_F32 ? 4 : 2;
+  const int NQ = (a.W + kCols - 1) / kCols;
+  int CB = 0;
+  for (int cb : {256, 128, 64})
+    if (NQ * cb / 2 <= 448 && (a.C % cb == 0 || (cb == 64 && a.C > 64))) { CB = cb; break; }
+  if (CB == 0) {
+    if (NQ * 32 <= 448) CB = 64; else return false;
+  }
+  if (a.act == MRLA_ACT_GELU && CB == 256) CB = 128;
+  p->cons_threads = NQ * (CB / 2);
+  p->big = p->cons_threads > 256;
+  const size_t ring = (size_t)4 * (NQ * kCols + 2) * (CB / 2) * sizeof(float2);
+  const size_t budget = (size_t)(p->big ? 200 : 100) * 1024;
+  if (ring + 8192 > budget) return false;
+  const uint32_t xrow = (uint32_t)(NQ * kCols + 2) * CB * es, trow = (uint32_t)(NQ * kCols) * CB * es;
+  const uint32_t rowtot = xrow + 2 * trow;
+  int G = (int)(((budget - ring) / 5) / rowtot);
+  if (G < 1) G = 1;
+  if (G > a.H) G = a.H;
+  p->CB = CB; p->NQ = NQ; p->NT = 1; p->WT = a.W; p->G = G;
+  p->x_bytes = (uint32_t)G * xrow;
+  p->t_bytes = (uint32_t)G * trow;
+  p->stage_bytes = p->x_bytes + 2 * p->t_bytes;
+  int S = (int)((budget - ring) / p->stage_bytes);
+  if (S > 8) S = 8;
+  if (S < 2) return false;
+  p->S = S;
+  p->ncb = (a.C + CB - 1) / CB;
+  p->items = p->ncb * a.B;
+  const int slots = p->big ? kNumSMs : 2 * kNumSMs;
+  int grid = p->items < slots ? p->items : slots;
+  p->ipc = (p->items + grid - 1) / grid;
+  p->grid = (p->items + p->ipc - 1) / p->ipc;
+  p->maxslots = (a.B + p->ipc - 1) / p->ipc + 1;
+  p->smem = 256 + (size_t)S * p->stage_bytes + ring;
+  return true;
+}
+
+template <typename T, int ACT>
+int launch_tma_bwd_ring(const MrlaLightArgs& a, cudaStream_t st, const TmaBwdPlan& p, float* wv_part) {
+  CUtensorMap tx, tdy, to;
+  if (make_nhwc_tmap(&tx, a.x, a.dtype, a.B, a.C, a.H, a.W, a.bs_x, p.CB, p.NQ * kCols + 2, p.G)) return MRLA_ERR_UNSUPPORTED;
+  if (make_nhwc_tmap(&tdy, a.dy, a.dtype, a.B, a.C, a.H, a.W, a.bs_dy, p.CB, p.NQ * kCols, p.G)) return MRLA_ERR_UNSUPPORTED;
+  if (make_nhwc_tmap(&to, a.o, a.dtype, a.B, a.C, a.H, a.W, a.bs_o, p.CB, p.NQ * kCols, p.G)) return MRLA_ERR_UNSUPPORTED;
+  cudaError_t e = cudaMemsetAsync(wv_part, 0, (size_t)p.maxslots * a.C * 9 * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  TmaBwdParams P;
+  P.B = a.B; P.C = a.C; P.H = a.H; P.W = a.W;
+  P.G = p.G; P.S = p.S; P.NQ = p.NQ; P.ncb = p.ncb; P.NT = 1; P.WT = a.W; P.items = p.items; P.ipc = p.ipc;
+  P.cons_threads = p.cons_threads; P.maxslots = p.maxslots;
+  P.x_bytes = p.x_bytes; P.t_bytes = p.t_bytes; P.stage_bytes = p.stage_bytes;
+  P.wv = a.wv; P.lam = a.lam; P.bcoef = a.bcoef; P.dx = a.dx; P.dout = a.dout; P.bs_dx = a.bs_dx; P.bs_do = a.bs_do;
+  P.res = a.residual ? 1.f : 0.f; P.wv_part = wv_part;
+  const int threads = 32 + p.cons_threads;
+#define MRLA_TMA_LAUNCH1(CBV, BIGV)                                                                       \
+  {                                                                                                       \
+    auto k = k_light_nhwc_tma_bwd_ring<T, CBV, ACT, BIGV>;                                                \
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);                \
+    if (e != cudaSuccess) return (int)e;                                                                  \
+    k<<<p.grid, threads, p.smem, st>>>(tx, tdy, to, P);                                                   \
+  }
+#define MRLA_TMA_LAUNCH(CBV)                                                                              \
+  {                                                                                                       \
+    if (p.big) MRLA_TMA_LAUNCH1(CBV, true) else MRLA_TMA_LAUNCH1(CBV, false)                              \
+  }
+  if (p.CB == 64) MRLA_TMA_LAUNCH(64)
+  else if (p.CB == 128) MRLA_TMA_LAUNCH(128)
+  else {
+    if (ACT == 1) return MRLA_ERR_UNSUPPORTED;
+    MRLA_TMA_LAUNCH(ACT == 1 ? 128 : 256)
+  }
+#undef MRLA_TMA_LAUNCH
+#undef MRLA_TMA_LAUNCH1
+  MRLA_CHECK_LAUNCH();
+  return MRLA_OK;
+}
+
 // ------------------------------------------------------------------------------------ forward
 template <typename T, int LAYOUT, int CV, int ACT, bool HAS_O>
 int light_forward_impl(const MrlaLightArgs& a, cudaStream_t st) {
@@ -316,7 +396,9 @@ int light_backward_impl(const MrlaLightArgs& a, cudaStream_t st) {
   const bool tma_b = LAYOUT == MRLA_NHWC && HAS_O && tma_ptr_ok(a.x, a.bs_x, es_) && tma_ptr_ok(a.o, a.bs_o, es_) &&
                      tma_ptr_ok(a.dy, a.bs_dy, es_) && (a.bs_dx * es_) % 4 == 0 && (a.bs_do * es_) % 4 == 0 &&
                      make_tma_bwd_plan(a, &tpb);
-  const int nparts = tma_b ? tpb.maxslots : pb.grid_y;
+  TmaBwdPlan tpr;
+  const bool tma_r = tma_b && make_tma_ring_plan(a, &tpr) && tpr.big;  // small images keep the halo-recompute kernel
+  const int nparts = tma_r ? tpr.maxslots : (tma_b ? tpb.maxslots : pb.grid_y);
   const size_t need = ((size_t)nparts * a.C * 9 + (size_t)a.B * 2 * a.k_size) * sizeof(float);
   if (a.scratch == nullptr || a.scratch_bytes < need) return MRLA_ERR_WORKSPACE;
   float* wv_part = a.scratch;
@@ -359,7 +441,10 @@ int light_backward_impl(const MrlaLightArgs& a, cudaStream_t st) {
     MRLA_CHECK_LAUNCH();
   }
   // sweep B
-  if (tma_b) {
+  if (tma_r) {
+    rc = launch_tma_bwd_ring<T, ACT>(a, st, tpr, wv_part);
+    if (rc) return rc;
+  } else if (tma_b) {
     rc = launch_tma_bwd<T, ACT>(a, st, tpb, wv_part);
     if (rc) return rc;
   } else {
@@ -415,6 +500,7 @@ inline size_t light_bwd_scratch_floats(const MrlaLightArgs& a) {
   int nparts = pb.grid_y;
   TmaBwdPlan tpb;
   if (make_tma_bwd_plan(a, &tpb) && tpb.maxslots > nparts) nparts = tpb.maxslots;
+  if (make_tma_ring_plan(a, &tpb) && tpb.maxslots > nparts) nparts = tpb.maxslots;
   return (size_t)nparts * a.C * 9 + (size_t)a.B * 2 * a.k_size;
 }
 

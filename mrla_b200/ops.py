@@ -81,6 +81,17 @@ def _f32(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return p.contiguous()
 
 
+def _like_param(g: torch.Tensor, meta) -> torch.Tensor:
+    """Shape / dtype / stride a flat fp32 gradient like its parameter.  `model.to(channels_last)` gives the
+    depthwise weight [C,1,3,3] strides (9,1,3,1): the memory order is that of the contiguous tensor (the
+    permuted dim has size 1), so only the stride metadata is adjusted — DDP's bucket views then match."""
+    shape, dtype, stride = meta
+    g = g.reshape(shape).to(dtype)
+    if g.stride() != stride and all(sz == 1 or a == b for sz, a, b in zip(shape, g.stride(), stride)):
+        g = g.as_strided(shape, stride)
+    return g
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -182,7 +193,8 @@ class _LightTail(torch.autograd.Function):
 
         ctx.cfg, ctx.layout, ctx.has_o = cfg, layout, has_o
         ctx.bs = (bs_x, bs_o)
-        ctx.param_meta = [(p.shape, p.dtype) if p is not None else None for p in (wq, wk, wv, lam, gamma, beta)]
+        ctx.param_meta = [(p.shape, p.dtype, p.stride()) if p is not None else None
+                          for p in (wq, wk, wv, lam, gamma, beta)]
         ctx.save_for_backward(x_c, o_c, wq32, wk32, wv32, lam32, ga32, ds32, mom, gate, stats)
         if out is not None:
             ctx.mark_dirty(out)
@@ -239,7 +251,7 @@ class _LightTail(torch.autograd.Function):
             meta = ctx.param_meta[i]
             if meta is None or g is None:
                 return None
-            return g.reshape(meta[0]).to(meta[1])
+            return _like_param(g, meta)
 
         grads = (dx, dout,
                  back(0, dwqk[0]), back(1, dwqk[1]), back(2, dwv),
@@ -370,7 +382,8 @@ class _BaseTail(torch.autograd.Function):
             running_var.copy_(rv)
         ctx.cfg, ctx.layout, ctx.cache, ctx.t, ctx.bs_x = cfg, layout, cache, t, bs_x
         ctx.has_ext = ext_k is not None
-        ctx.param_meta = [(q_.shape, q_.dtype) if q_ is not None else None for q_ in (wq, wk, wv, gamma, beta)]
+        ctx.param_meta = [(q_.shape, q_.dtype, q_.stride()) if q_ is not None else None
+                          for q_ in (wq, wk, wv, gamma, beta)]
         ctx.ext_meta = (ext_k.dtype, ext_v.dtype) if ctx.has_ext else None
         ctx.save_for_backward(x_c, s, wq32, wk32, wv32, ga32, ds32, sxq, p, chan)
         ctx.has_token = token is not None
@@ -429,7 +442,7 @@ class _BaseTail(torch.autograd.Function):
 
         def back(i, g_):
             meta = ctx.param_meta[i]
-            return None if meta is None or g_ is None else g_.reshape(meta[0]).to(meta[1])
+            return None if meta is None or g_ is None else _like_param(g_, meta)
 
         dk_ext = dv_ext = None
         if ctx.has_ext:
