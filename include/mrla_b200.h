@@ -184,6 +184,11 @@ size_t mrla_base_bwd_scratch_bytes(const MrlaBaseArgs* a);
 int mrla_base_forward(const MrlaBaseArgs* a, void* stream);
 int mrla_base_backward(const MrlaBaseArgs* a, void* stream);
 
+/* Repack a dense NCHW activation [B,C,HW] (batch stride bs_src elements) into NHWC [B,HW,C] (batch stride bs_dst).
+ * Used to promote NCHW callers onto the TMA (channels_last) kernels; replaces at::contiguous(channels_last). */
+int mrla_nchw_to_nhwc(const void* src, void* dst, int B, int C, int HW, int dtype, int64_t bs_src, int64_t bs_dst,
+                      void* stream);
+
 /* Number of kernel launches the last forward / backward call on this thread enqueued
  * (bench.py reports it as gpu_launches). */
 int mrla_last_launch_count(void);

@@ -63,7 +63,7 @@ _lock = threading.Lock()
 EXPORTS = (
     "mrla_abi_version", "mrla_build_info", "mrla_last_launch_count", "mrla_sizeof_light_args",
     "mrla_light_bwd_scratch_bytes", "mrla_light_forward", "mrla_light_backward",
-    "mrla_sizeof_base_args", "mrla_base_bwd_scratch_bytes", "mrla_base_forward", "mrla_base_backward",
+    "mrla_nchw_to_nhwc", "mrla_sizeof_base_args", "mrla_base_bwd_scratch_bytes", "mrla_base_forward", "mrla_base_backward",
 )
 
 
@@ -89,6 +89,9 @@ def lib() -> ctypes.CDLL:
         L.mrla_sizeof_light_args.restype = ctypes.c_size_t
         if L.mrla_sizeof_light_args() != ctypes.sizeof(MrlaLightArgs):
             raise RuntimeError("MrlaLightArgs layout mismatch between _lib.py and include/mrla_b200.h")
+        L.mrla_nchw_to_nhwc.restype = ctypes.c_int
+        L.mrla_nchw_to_nhwc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]
         L.mrla_sizeof_base_args.restype = ctypes.c_size_t
         if L.mrla_sizeof_base_args() != ctypes.sizeof(MrlaBaseArgs):
             raise RuntimeError("MrlaBaseArgs layout mismatch between _lib.py and include/mrla_b200.h")

@@ -1,0 +1,44 @@
+// NCHW -> NHWC repack used when a dense NCHW activation is promoted to the TMA (channels_last) kernels.
+// Classic shared-memory tile transpose of the [C, HW] matrix of every sample: coalesced reads along HW,
+// coalesced 2-element stores along C.
+#pragma once
+#include "common.cuh"
+
+namespace mrla {
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_nchw_to_nhwc(const T* __restrict__ src, T* __restrict__ dst, int C, int HW,
+                                                      int64_t bs_src, int64_t bs_dst) {
+  constexpr int TILE = 64;
+  __shared__ T tile[TILE][TILE + 2];
+  const int b = blockIdx.z;
+  const int hw0 = blockIdx.x * TILE, c0 = blockIdx.y * TILE;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const T* s = src + (int64_t)b * bs_src;
+  T* d = dst + (int64_t)b * bs_dst;
+#pragma unroll
+  for (int i = 0; i < TILE / 8; ++i) {
+    const int c = c0 + warp + i * 8;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int hw = hw0 + lane + 32 * k;
+      if (c < C && hw < HW) tile[warp + i * 8][lane + 32 * k] = s[(int64_t)c * HW + hw];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < TILE / 8; ++i) {
+    const int hw = hw0 + warp + i * 8;
+    const int c = c0 + 2 * lane;
+    if (hw < HW && c + 1 < C) {
+      Pack<T, 2> pk;
+      pk.v[0] = tile[2 * lane][warp + i * 8];
+      pk.v[1] = tile[2 * lane + 1][warp + i * 8];
+      *reinterpret_cast<Pack<T, 2>*>(d + (int64_t)hw * C + c) = pk;
+    } else if (hw < HW && c < C) {
+      d[(int64_t)hw * C + c] = tile[2 * lane][warp + i * 8];
+    }
+  }
+}
+
+}  // namespace mrla

@@ -1,5 +1,6 @@
 // extern "C" entry points of libmrla_b200.so (see include/mrla_b200.h).
 #include "base_launch.cuh"
+#include "layout_kernels.cuh"
 
 namespace mrla {
 thread_local int g_launch_count = 0;
@@ -118,6 +119,23 @@ int mrla_light_backward(const MrlaLightArgs* a, void* stream) {
     case MRLA_BF16: return light_backward_t<__nv_bfloat16>(*a, st);
     default: return light_backward_t<__half>(*a, st);
   }
+}
+
+int mrla_nchw_to_nhwc(const void* src, void* dst, int B, int C, int HW, int dtype, int64_t bs_src, int64_t bs_dst,
+                      void* stream) {
+  g_launch_count = 0;
+  if (!src || !dst) return MRLA_ERR_NULL;
+  if (B < 1 || C < 1 || HW < 1 || B > 65535) return MRLA_ERR_SHAPE;
+  if (dtype < MRLA_F32 || dtype > MRLA_F16) return MRLA_ERR_UNSUPPORTED;
+  if (C % 2 || ((uintptr_t)dst % (2 * esize(dtype))) || bs_dst % 2) return MRLA_ERR_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 grid((HW + 63) / 64, (C + 63) / 64, B);
+  if (dtype == MRLA_F32)
+    k_nchw_to_nhwc<float><<<grid, 256, 0, st>>>(static_cast<const float*>(src), static_cast<float*>(dst), C, HW, bs_src, bs_dst);
+  else
+    k_nchw_to_nhwc<uint16_t><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(src), static_cast<uint16_t*>(dst), C, HW, bs_src, bs_dst);
+  MRLA_CHECK_LAUNCH();
+  return MRLA_OK;
 }
 
 size_t mrla_sizeof_base_args(void) { return sizeof(MrlaBaseArgs); }

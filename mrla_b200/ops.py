@@ -133,6 +133,40 @@ class _Prof:
 
 launch_counter = {"fwd": 0, "bwd": 0}
 
+# The TMA-pipelined kernels are NHWC.  A dense NCHW activation that is large enough to matter is therefore
+# promoted to channels_last on first contact (one library copy per tensor); the result comes back channels_last,
+# so everything downstream (cuDNN convs, the next tails) stays in the fast layout and pays nothing.  Small or
+# TMA-ineligible NCHW inputs, and PROMOTE_NCHW = False, use the generic NCHW kernels directly.
+PROMOTE_NCHW = True
+PROMOTE_MIN_ELEMS = 1 << 20
+
+
+def _to_nhwc(t: torch.Tensor) -> torch.Tensor:
+    """Dense NCHW -> channels_last copy through the library's tiled-transpose kernel."""
+    B, C, H, W = t.shape
+    out = torch.empty((B, H, W, C), dtype=t.dtype, device=t.device).permute(0, 3, 1, 2)
+    L = _lib.lib()
+    _lib.check(L.mrla_nchw_to_nhwc(t.data_ptr(), out.data_ptr(), B, C, H * W, _DTYPES[t.dtype], t.stride(0),
+                                   C * H * W, _stream()), "mrla_nchw_to_nhwc")
+    return out
+
+
+class _ToNHWC(torch.autograd.Function):
+    """Differentiable wrapper: the gradient simply flows back in whatever layout it arrives."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return _to_nhwc(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _want_nhwc(x: torch.Tensor) -> bool:
+    B, C, H, W = x.shape
+    return PROMOTE_NCHW and x.numel() >= PROMOTE_MIN_ELEMS and C % 8 == 0 and W <= 56 and H * W > 1
+
 
 # --------------------------------------------------------------------------------- the fused op
 class _LightTail(torch.autograd.Function):
@@ -141,13 +175,20 @@ class _LightTail(torch.autograd.Function):
         _require_cuda(x, "x")
         L = _lib.lib()
         x_c, layout, bs_x = _canon(x)
-        B, C, H, W = x_c.shape
         has_o = o is not None
+        promote = layout == _lib.NCHW and has_o and out is None and _want_nhwc(x_c)
+        if promote:
+            x_c, layout, bs_x = _to_nhwc(x_c), _lib.NHWC, x_c[0].numel()
+        B, C, H, W = x_c.shape
         if has_o:
             _require_cuda(o, "o")
             if o.shape != x.shape or o.dtype != x.dtype:
                 raise RuntimeError("mrla_b200: o_prev must match x in shape and dtype")
-            o_c, _, bs_o = _canon(o, layout)
+            lay_o = _layout_of(o)
+            if promote and lay_o is not None and lay_o[0] == _lib.NCHW and o.stride(1) == H * W:
+                o_c, bs_o = _to_nhwc(o), C * H * W
+            else:
+                o_c, _, bs_o = _canon(o, layout)
         else:
             o_c, bs_o = None, 0
         if out is not None:
@@ -206,9 +247,13 @@ class _LightTail(torch.autograd.Function):
         x_c, o_c, wq32, wk32, wv32, lam32, ga32, ds32, mom, gate, stats = ctx.saved_tensors
         cfg, layout = ctx.cfg, ctx.layout
         B, C, H, W = x_c.shape
-        dy_c, _, bs_dy = _canon(dy, layout)
-        if dy_c.dtype != x_c.dtype:
-            dy_c = dy_c.to(x_c.dtype)
+        if dy.dtype != x_c.dtype:
+            dy = dy.to(x_c.dtype)
+        lay_dy = _layout_of(dy)
+        if layout == _lib.NHWC and lay_dy is not None and lay_dy[0] == _lib.NCHW and C % 2 == 0 and H * W > 1:
+            dy_c, bs_dy = _to_nhwc(dy), C * H * W
+        else:
+            dy_c, _, bs_dy = _canon(dy, layout)
         dx = _empty_like_layout(x_c, layout)
         dout = _empty_like_layout(x_c, layout) if ctx.has_o else None
         dev = x_c.device

@@ -94,12 +94,17 @@ def _oracle_tail_fp64(x, o, P, d, drop_scale, dy, training=True):
     return y.detach(), xd.grad, od.grad, {k: v.grad for k, v in Pd.items()}, rm, rv
 
 
-@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("layout", LAYOUTS + ["nchw_generic"])
 @pytest.mark.parametrize("dtype,B", [(torch.float32, 32), (torch.bfloat16, 256)])
 @pytest.mark.parametrize("C,HW", STAGES)
-def test_light_tail_stage_shapes_vs_oracle(C, HW, dtype, B, layout, cuda_device):
-    """BASELINE.json stage shapes: config-1 batch (32, fp32) and config-2 batch (256/GPU, bf16)."""
-    from mrla_b200 import _lib
+def test_light_tail_stage_shapes_vs_oracle(C, HW, dtype, B, layout, cuda_device, monkeypatch):
+    """BASELINE.json stage shapes: config-1 batch (32, fp32) and config-2 batch (256/GPU, bf16).
+    `nchw` inputs of this size are promoted to channels_last inside the op (TMA kernels); `nchw_generic`
+    pins the generic NCHW kernels on the same inputs."""
+    from mrla_b200 import _lib, ops
+    if layout == "nchw_generic":
+        monkeypatch.setattr(ops, "PROMOTE_NCHW", False)
+        layout = "nchw"
     from mrla_b200.modules.mrla_light_module import eca_kernel_size
     from mrla_b200.ops import LightCfg, light_tail
     dev = cuda_device
