@@ -177,9 +177,13 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 #pragma unroll
   for (int j = 0; j < kCols; ++j) cvalid[j] = (q * kCols + j) < P.W;
 
-  int st_cur = 0;        // stage of the group that holds x row r
+  // ring cursor: shared-memory address of the next x row / its o(dy) row, advanced incrementally so the row
+  // loop carries no multiplies or divisions
+  int st_cur = 0;
   uint32_t ph_cur = 0;
-  int st_prev = 0;       // stage of the group that holds row r-1
+  int rr = 0;
+  uint32_t xa = stages_s + tbase;                 // address of x row r (window column 0 of this thread)
+  uint32_t oa = stages_s + P.x_bytes + tbase;     // address of o row r
 
   for (int item = blockIdx.x; item < P.items; item += gridDim.x) {
     const int b = item / P.ncb, cb = item - b * P.ncb;
@@ -204,36 +208,46 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     // running pointer to this thread's first output column of the row being produced
     T* yrow = (MODE == 1) ? static_cast<T*>(P.y) + (int64_t)b * P.bs_y + (int64_t)(q * kCols) * P.C + c : nullptr;
     const int64_t y_row_stride = (int64_t)P.W * P.C;
+    bool sv[kCols];
+#pragma unroll
+    for (int j = 0; j < kCols; ++j) sv[j] = chan_ok && cvalid[j];
 
     float2 win[3][kWin];
 #pragma unroll
     for (int j = 0; j < kWin; ++j) win[2][j] = f2(0.f, 0.f);  // row -1 lives in slot 2
 
-    int rr = 0;  // row index of r inside its group
+    uint32_t o_prev = 0;      // address of the o(dy) row of the previous x row
+    int rel_stage = -1;       // stage to release once the previous row has been consumed (-1: none)
     // r = x row being fetched into the window; output row r-1 is produced in the same step
     for (int r0 = 0; r0 <= P.H; r0 += 3) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         const int r = r0 + i;
         if (r <= P.H) {
+          uint32_t o_this = 0;
+          int rel_next = -1;
           // ---- fetch x row r into window slot i ----
           if (r < P.H) {
             if (rr == 0) mbar_wait(&full[st_cur], ph_cur);
-            const uint32_t rowb = stages_s + (uint32_t)st_cur * P.stage_bytes + (uint32_t)rr * xrow_bytes + tbase;
 #pragma unroll
-            for (int j = 0; j < kWin; ++j) win[i][j] = lds_pair<T>(rowb + j * CS);
+            for (int j = 0; j < kWin; ++j) win[i][j] = lds_pair<T>(xa + j * CS);
+            o_this = oa;
+            xa += xrow_bytes;
+            oa += orow_bytes;
+            if (++rr == P.G || r == P.H - 1) {   // last row of its group: move the cursor to the next stage
+              rel_next = st_cur;
+              rr = 0;
+              if (++st_cur == P.S) { st_cur = 0; ph_cur ^= 1; }
+              xa = stages_s + (uint32_t)st_cur * P.stage_bytes + tbase;
+              oa = xa + P.x_bytes;
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < kWin; ++j) win[i][j] = f2(0.f, 0.f);
           }
           // ---- produce output row r-1 ----
           if (r >= 1) {
-            const int ro = r - 1;
-            const int rro = (rr == 0) ? (P.G - 1) : rr - 1;           // its row inside its group
-            const int sto = (rr == 0) ? st_prev : st_cur;
-            const int rro_fix = (r == P.H) ? ((P.H - 1) % P.G) : rro;  // last image row may sit in a short group
-            const int sto_fix = (r == P.H) ? st_prev : sto;
-            const uint32_t ob = stages_s + (uint32_t)sto_fix * P.stage_bytes + P.x_bytes + (uint32_t)rro_fix * orow_bytes + tbase;
+            const uint32_t ob = o_prev;
             const float2(&top)[kWin] = win[(i + 1) % 3];
             const float2(&mid)[kWin] = win[(i + 2) % 3];
             const float2(&bot)[kWin] = win[i];
@@ -265,24 +279,18 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 float2 t = ffma2(cA, v, cD);
                 if (HAS_O) t = ffma2(cL, ov, t);
                 t = ffma2(res2, xc, t);
-                if (chan_ok && cvalid[j]) stg_pair<T>(yrow + j * P.C, t);
+                if (sv[j]) stg_pair<T>(yrow + j * P.C, t);
               }
             }
             if (MODE == 1) yrow += y_row_stride;
             // release the group whose last row was just consumed
-            if (rro_fix == P.G - 1 || ro == P.H - 1) {
+            if (rel_stage >= 0) {
               __syncwarp();
-              if (lane == 0) mbar_arrive(&empty[sto_fix]);
+              if (lane == 0) mbar_arrive(&empty[rel_stage]);
             }
           }
-          // ---- advance the row-in-group cursor ----
-          if (r < P.H) {
-            if (++rr == P.G || r == P.H - 1) {
-              rr = 0;
-              st_prev = st_cur;
-              if (++st_cur == P.S) { st_cur = 0; ph_cur ^= 1; }
-            }
-          }
+          o_prev = o_this;
+          rel_stage = rel_next;
         }
       }
     }
@@ -680,8 +688,11 @@ k_light_nhwc_tma_bwd_ring(const __grid_constant__ CUtensorMap tm_x, const __grid
   }
   named_bar_sync(1, P.cons_threads);
 
-  int st_cur = 0, st_prev = 0;
+  int st_cur = 0;
   uint32_t ph_cur = 0;
+  int rr = 0;
+  uint32_t xa = stages_s + tbase;                 // address of x row r
+  uint32_t ta_ = stages_s + P.x_bytes + tbase;    // address of dy row r (o row = + t_bytes)
   int cur_cb = -1;
   float2 dw[9];
 #pragma unroll
@@ -760,18 +771,33 @@ k_light_nhwc_tma_bwd_ring(const __grid_constant__ CUtensorMap tm_x, const __grid
     for (int k = 0; k < kWin; ++k) xw[2][k] = f2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < kCols; ++j) dyprev[j] = f2(0.f, 0.f);
-    int rr = 0;
+    bool sv[kCols];
+#pragma unroll
+    for (int j = 0; j < kCols; ++j) sv[j] = chan_ok && cvalid[j];
+    uint32_t t_prev = 0;
+    int rel_stage = -1;
     for (int r0 = 0; r0 <= P.H + 1; r0 += 3) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         const int r = r0 + i;
         if (r <= P.H + 1) {
+          uint32_t t_this = 0;
+          int rel_next = -1;
           // ---- fetch x row r ----
           if (r < P.H) {
             if (rr == 0) mbar_wait(&full[st_cur], ph_cur);
-            const uint32_t rowb = stages_s + (uint32_t)st_cur * P.stage_bytes + (uint32_t)rr * xrow_bytes + tbase;
 #pragma unroll
-            for (int k = 0; k < kWin; ++k) xw[i][k] = lds_pair<T>(rowb + k * CS);
+            for (int k = 0; k < kWin; ++k) xw[i][k] = lds_pair<T>(xa + k * CS);
+            t_this = ta_;
+            xa += xrow_bytes;
+            ta_ += trow_bytes;
+            if (++rr == P.G || r == P.H - 1) {
+              rel_next = st_cur;
+              rr = 0;
+              if (++st_cur == P.S) { st_cur = 0; ph_cur ^= 1; }
+              xa = stages_s + (uint32_t)st_cur * P.stage_bytes + tbase;
+              ta_ = xa + P.x_bytes;
+            }
           } else {
 #pragma unroll
             for (int k = 0; k < kWin; ++k) xw[i][k] = f2(0.f, 0.f);
@@ -782,9 +808,7 @@ k_light_nhwc_tma_bwd_ring(const __grid_constant__ CUtensorMap tm_x, const __grid
           // ---- T row t = r-1 ----
           if (r >= 1 && r <= P.H) {
             const int t = r - 1;
-            const int rro = (r == P.H) ? ((P.H - 1) % P.G) : ((rr == 0) ? (P.G - 1) : rr - 1);
-            const int sto = (r == P.H || rr == 0) ? st_prev : st_cur;
-            const uint32_t tb = stages_s + (uint32_t)sto * P.stage_bytes + P.x_bytes + (uint32_t)rro * trow_bytes + tbase;
+            const uint32_t tb = t_prev;
             const float2(&top)[kWin] = xw[(i + 1) % 3];
             const float2(&mid)[kWin] = xw[(i + 2) % 3];
             const float2(&bot)[kWin] = xw[i];
@@ -804,7 +828,7 @@ k_light_nhwc_tma_bwd_ring(const __grid_constant__ CUtensorMap tm_x, const __grid
               if (ragged && !cvalid[j]) tt = f2(0.f, 0.f);
               dycur[j] = gy;
               asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(rslot + j * TS), "f"(tt.x), "f"(tt.y) : "memory");
-              if (chan_ok && cvalid[j]) stg_pair<T>(dop + j * P.C, fmul2(lm, ds));
+              if (sv[j]) stg_pair<T>(dop + j * P.C, fmul2(lm, ds));
               dw[0] = ffma2(tt, top[j], dw[0]);
               dw[1] = ffma2(tt, top[j + 1], dw[1]);
               dw[2] = ffma2(tt, top[j + 2], dw[2]);
@@ -816,11 +840,13 @@ k_light_nhwc_tma_bwd_ring(const __grid_constant__ CUtensorMap tm_x, const __grid
               dw[8] = ffma2(tt, bot[j + 2], dw[8]);
             }
             dop += row_stride;
-            if (rro == P.G - 1 || t == P.H - 1) {
+            if (rel_stage >= 0) {
               __syncwarp();
-              if (lane == 0) mbar_arrive(&empty[sto]);
+              if (lane == 0) mbar_arrive(&empty[rel_stage]);
             }
           }
+          t_prev = t_this;
+          rel_stage = rel_next;
           named_bar_sync(1, P.cons_threads);
           // ---- dX row h = r-2 from T rows r-3, r-2, r-1 ----
           if (r >= 2) {
@@ -847,18 +873,11 @@ k_light_nhwc_tma_bwd_ring(const __grid_constant__ CUtensorMap tm_x, const __grid
             }
 #pragma unroll
             for (int j = 0; j < kCols; ++j)
-              if (chan_ok && cvalid[j]) stg_pair<T>(dxp + j * P.C, acc[j]);
+              if (sv[j]) stg_pair<T>(dxp + j * P.C, acc[j]);
             dxp += row_stride;
           }
 #pragma unroll
           for (int j = 0; j < kCols; ++j) dyprev[j] = dycur[j];
-          if (r < P.H) {
-            if (++rr == P.G || r == P.H - 1) {
-              rr = 0;
-              st_prev = st_cur;
-              if (++st_cur == P.S) { st_cur = 0; ph_cur ^= 1; }
-            }
-          }
         }
       }
     }
