@@ -414,7 +414,6 @@ static __global__ void __launch_bounds__(1024) k_base_bwd_attn(const float* __re
   float* dq = sm + C;
   float* dk = sm + 2 * C;
   float* dl = sm + 3 * C;
-  __shared__ float wred[32];
   const int b = blockIdx.x;
   const int g = C / d;
   const int64_t BC = (int64_t)B * C;
@@ -459,23 +458,16 @@ static __global__ void __launch_bounds__(1024) k_base_bwd_attn(const float* __re
     dyc[(int64_t)b * C + c] = acc * inv_hw;
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int j = 0; j < 2 * k; ++j) {
+  for (int j = wid; j < 2 * k; j += nw) {
     const int jj = (j < k) ? j : j - k;
     const float* src = (j < k) ? dq : dk;
     float acc = 0.f;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    for (int c = lane; c < C; c += 32) {
       const int cc = c + jj - pad;
       if (cc >= 0 && cc < C) acc = fmaf(ys[cc], src[c], acc);
     }
     acc = warp_sum(acc);
-    __syncthreads();
-    if (lane == 0) wred[wid] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float tt = 0.f;
-      for (int i = 0; i < nw; ++i) tt += wred[i];
-      wqk_part[(int64_t)b * 2 * k + j] = tt;
-    }
+    if (lane == 0) wqk_part[(int64_t)b * 2 * k + j] = acc;
   }
 }
 

@@ -120,7 +120,7 @@ int base_backward_impl(const MrlaBaseArgs& a, cudaStream_t st) {
   // B5
   {
     const int total = a.C * 9 + 2 * a.k_size;
-    k_light_finish<<<(total + 255) / 256, 256, 0, st>>>(wv_part, p.grid_y, wqk_part, a.dwv, a.dwq, a.dwk, a.B, a.C,
+    k_light_finish<<<(a.C * 9 + 255) / 256 + (2 * a.k_size + 7) / 8, 256, 0, st>>>(wv_part, p.grid_y, wqk_part, a.dwv, a.dwq, a.dwk, a.B, a.C,
                                                          a.k_size);
     MRLA_CHECK_LAUNCH();
   }

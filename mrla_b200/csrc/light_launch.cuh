@@ -102,7 +102,7 @@ inline bool make_tma_plan(const MrlaLightArgs& a, int ntiles, int nacc, TmaPlan*
   p->x_bytes = (uint32_t)G * xrow;
   p->o_bytes = (uint32_t)G * orow;
   p->stage_bytes = p->x_bytes + (uint32_t)ntiles * p->o_bytes;
-  const size_t red = (size_t)NQ * nacc * (CB / 2) * sizeof(float2);
+  const size_t red = (size_t)2 * NQ * nacc * (CB / 2) * sizeof(float2);   // double buffered
   int S = (int)((budget - red) / p->stage_bytes);
   if (S > 8) S = 8;
   if (S < 2) return false;
@@ -111,6 +111,7 @@ inline bool make_tma_plan(const MrlaLightArgs& a, int ntiles, int nacc, TmaPlan*
   p->items = a.B * p->ncb;
   const int slots = p->big ? kNumSMs : 2 * kNumSMs;
   p->grid = p->items < slots ? p->items : slots;
+  if (p->grid >= p->ncb) p->grid -= p->grid % p->ncb;   // a CTA then always sees the same channel block
   p->smem = 256 + (size_t)S * p->stage_bytes + red;
   return true;
 }
@@ -461,7 +462,7 @@ int light_backward_impl(const MrlaLightArgs& a, cudaStream_t st) {
   // final reductions
   {
     const int total = a.C * 9 + 2 * a.k_size;
-    k_light_finish<<<(total + 255) / 256, 256, 0, st>>>(wv_part, nparts, wqk_part, a.dwv, a.dwq, a.dwk, a.B, a.C,
+    k_light_finish<<<(a.C * 9 + 255) / 256 + (2 * a.k_size + 7) / 8, 256, 0, st>>>(wv_part, nparts, wqk_part, a.dwv, a.dwq, a.dwk, a.B, a.C,
                                                          a.k_size);
     MRLA_CHECK_LAUNCH();
   }

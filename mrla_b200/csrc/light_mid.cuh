@@ -73,6 +73,7 @@ static __global__ void __launch_bounds__(1024) k_light_bn_coef(const float* __re
   if (s.bn_mode == 1) {
     double s1 = 0.0, s2 = 0.0;
     if (cok) {
+#pragma unroll 4
       for (int b = bl; b < s.B; b += 32) {
         const int64_t i = (int64_t)b * s.C + c;
         const double a = gate[(int64_t)b * g + c / s.d];
@@ -167,6 +168,7 @@ static __global__ void __launch_bounds__(1024) k_light_bwd_chan(const float* __r
   // pass 1: dβ, dγ
   double s1 = 0.0, s2 = 0.0;
   if (cok && s.bn_mode != 0) {
+#pragma unroll 4
     for (int b = bl; b < s.B; b += 32) {
       const int64_t i = (int64_t)b * s.C + c;
       const double mb = drop_scale ? (double)drop_scale[b] : 1.0;
@@ -199,6 +201,7 @@ static __global__ void __launch_bounds__(1024) k_light_bwd_chan(const float* __r
   // pass 2: dλ, da[b,c], sweep-B coefficients
   double sl = 0.0;
   if (cok) {
+#pragma unroll 4
     for (int b = bl; b < s.B; b += 32) {
       const int64_t i = (int64_t)b * s.C + c;
       const double mb = drop_scale ? (double)drop_scale[b] : 1.0;
@@ -250,7 +253,6 @@ static __global__ void __launch_bounds__(1024) k_light_bwd_gate(const float* __r
   float* dq = sm + 3 * s.C;
   float* dk = sm + 4 * s.C;
   float* dl = sm + 5 * s.C;
-  __shared__ float wred[32];
   const int b = blockIdx.x;
   const int g = s.C / s.d;
   const int64_t BC = (int64_t)s.B * s.C;
@@ -291,45 +293,46 @@ static __global__ void __launch_bounds__(1024) k_light_bwd_gate(const float* __r
     }
     bcoef[5 * BC + (int64_t)b * s.C + c] = acc * inv_hw;
   }
-  // dwq[j] = Σ_c y[c+j-pad] dQ[c], dwk likewise: block reduction per tap (k <= 15)
+  // dwq[j] = Σ_c y[c+j-pad] dQ[c], dwk likewise: one warp per tap (k <= 15), no block barriers
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int j = 0; j < 2 * s.k; ++j) {
+  for (int j = wid; j < 2 * s.k; j += nw) {
     const int jj = (j < s.k) ? j : j - s.k;
     const float* src = (j < s.k) ? dq : dk;
     float acc = 0.f;
-    for (int c = threadIdx.x; c < s.C; c += blockDim.x) {
+    for (int c = lane; c < s.C; c += 32) {
       const int cc = c + jj - pad;
       if (cc >= 0 && cc < s.C) acc = fmaf(ys[cc], src[c], acc);
     }
     acc = warp_sum(acc);
-    __syncthreads();
-    if (lane == 0) wred[wid] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float t = 0.f;
-      for (int i = 0; i < nw; ++i) t += wred[i];
-      wqk_part[(int64_t)b * 2 * s.k + j] = t;
-    }
+    if (lane == 0) wqk_part[(int64_t)b * 2 * s.k + j] = acc;
   }
 }
 
 // --------------------------------------------------------------------------------- final reductions
-// dwv[c,tap] = Σ_p wv_part[p,c,tap] ; dwq[j] = Σ_b wqk_part[b,j] ; dwk[j] = Σ_b wqk_part[b,k+j]
+// dwv[c,tap] = Σ_p wv_part[p,c,tap] (one thread per output) ; dwq[j] = Σ_b wqk_part[b,j], dwk[j] = Σ_b wqk_part[b,k+j]
+// (one warp per tap: strided loads + shuffle tree instead of a B-long dependent chain)
 static __global__ void k_light_finish(const float* __restrict__ wv_part, int nparts, const float* __restrict__ wqk_part,
-                               float* __restrict__ dwv, float* __restrict__ dwq, float* __restrict__ dwk, int B, int C,
-                               int k) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                      float* __restrict__ dwv, float* __restrict__ dwq, float* __restrict__ dwk, int B,
+                                      int C, int k) {
   const int64_t n1 = (int64_t)C * 9;
-  if (idx < n1) {
-    if (dwv != nullptr) {
+  const int nb1 = (int)((n1 + blockDim.x - 1) / blockDim.x);
+  if ((int)blockIdx.x < nb1) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n1 && dwv != nullptr) {
       float acc = 0.f;
       for (int p = 0; p < nparts; ++p) acc += wv_part[(int64_t)p * n1 + idx];
       dwv[idx] = acc;
     }
-  } else if (idx < n1 + 2 * k) {
-    const int j = (int)(idx - n1);
-    float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc += wqk_part[(int64_t)b * 2 * k + j];
+    return;
+  }
+  const int warps_per_block = blockDim.x >> 5;
+  const int j = ((int)blockIdx.x - nb1) * warps_per_block + (threadIdx.x >> 5);
+  if (j >= 2 * k) return;
+  const int lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int b = lane; b < B; b += 32) acc += wqk_part[(int64_t)b * 2 * k + j];
+  acc = warp_sum(acc);
+  if (lane == 0) {
     if (j < k) { if (dwq) dwq[j] = acc; }
     else { if (dwk) dwk[j - k] = acc; }
   }

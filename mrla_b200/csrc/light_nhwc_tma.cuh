@@ -122,7 +122,7 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* empty = full + 16;
   unsigned char* stages = smem_raw + 256;
-  float2* red = reinterpret_cast<float2*>(stages + (size_t)P.S * P.stage_bytes);  // [NQ][NACC][NP]
+  float2* red_base = reinterpret_cast<float2*>(stages + (size_t)P.S * P.stage_bytes);  // [2][NQ][NACC][NP]
   const int ncw = P.cons_threads / 32;
 
   if (threadIdx.x == 0) {
@@ -184,15 +184,20 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   int rr = 0;
   uint32_t xa = stages_s + tbase;                 // address of x row r (window column 0 of this thread)
   uint32_t oa = stages_s + P.x_bytes + tbase;     // address of o row r
+  int cur_cb = -1;   // the grid is a multiple of ncb, so a CTA keeps its channel block: weights are loaded once
+  float2 w9[9];
+  int red_sel = 0;   // double-buffered reduction scratch: one consumer barrier per image
 
   for (int item = blockIdx.x; item < P.items; item += gridDim.x) {
     const int b = item / P.ncb, cb = item - b * P.ncb;
     const int c = cb * CB + 2 * p;
     const bool chan_ok = c < P.C;
-    float2 w9[9];
+    if (cb != cur_cb) {
+      cur_cb = cb;
 #pragma unroll
-    for (int i = 0; i < 9; ++i)
-      w9[i] = chan_ok ? f2(P.wv[(int64_t)c * 9 + i], P.wv[(int64_t)(c + 1) * 9 + i]) : f2(0.f, 0.f);
+      for (int i = 0; i < 9; ++i)
+        w9[i] = chan_ok ? f2(P.wv[(int64_t)c * 9 + i], P.wv[(int64_t)(c + 1) * 9 + i]) : f2(0.f, 0.f);
+    }
     float2 cA = f2(0.f, 0.f), cL = f2(0.f, 0.f), cD = f2(0.f, 0.f);
     if (MODE == 1 && chan_ok) {
       const int64_t BC = (int64_t)P.B * P.C;
@@ -296,7 +301,11 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     }
 
     if (NACC > 0) {
-      // deterministic reduction over the NQ column groups of every channel pair
+      // deterministic reduction over the NQ column groups of every channel pair.  The scratch is double
+      // buffered: a thread can only reach the write of image i+2 after the barrier of image i+1, which every
+      // thread passes after finishing its reads of image i.
+      float2* red = red_base + (size_t)red_sel * P.NQ * NACC * NP;
+      red_sel ^= 1;
 #pragma unroll
       for (int i = 0; i < NACC; ++i) red[((size_t)q * NACC + i) * NP + p] = fadd2(acc[i], accb[i]);
       named_bar_sync(1, P.cons_threads);
@@ -312,7 +321,6 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const int cc = cb * CB + 2 * pp;
         if (cc < P.C) *reinterpret_cast<float2*>(P.mom + (int64_t)mi * BC + (int64_t)b * P.C + cc) = s;
       }
-      named_bar_sync(1, P.cons_threads);
     }
   }
 }
