@@ -250,17 +250,19 @@ inline bool make_tma_ring_plan(const MrlaLightArgs& a, TmaBwdPlan* p) {
   if (a.layout != MRLA_NHWC || a.C % 8 || a.W > 56) return false;
   const int es = a.dtype == MRLA_F32 ? 4 : 2;
   const int NQ = (a.W + kCols - 1) / kCols;
+  // big: one CTA of up to 448 consumers per SM; small: up to 128 consumers, three CTAs per SM
   int CB = 0;
   for (int cb : {256, 128, 64})
-    if (NQ * cb / 2 <= 448 && (a.C % cb == 0 || (cb == 64 && a.C > 64))) { CB = cb; break; }
-  if (CB == 0) {
-    if (NQ * 32 <= 448) CB = 64; else return false;
-  }
-  if (a.act == MRLA_ACT_GELU && CB == 256) CB = 128;
+    if (NQ * cb / 2 <= 448 && NQ * cb / 2 > 256 && a.C % cb == 0) { CB = cb; break; }
+  if (CB == 0)
+    for (int cb : {256, 128, 64})
+      if (NQ * cb / 2 <= 128 && (a.C % cb == 0 || cb == 64)) { CB = cb; break; }
+  if (CB == 0) return false;
+  if (a.act == MRLA_ACT_GELU && CB == 256) return false;
   p->cons_threads = NQ * (CB / 2);
   p->big = p->cons_threads > 256;
   const size_t ring = (size_t)4 * (NQ * kCols + 2) * (CB / 2) * sizeof(float2);
-  const size_t budget = (size_t)(p->big ? 200 : 100) * 1024;
+  const size_t budget = (size_t)(p->big ? 200 : 66) * 1024;
   if (ring + 8192 > budget) return false;
   const uint32_t xrow = (uint32_t)(NQ * kCols + 2) * CB * es, trow = (uint32_t)(NQ * kCols) * CB * es;
   const uint32_t rowtot = xrow + 2 * trow;
@@ -277,7 +279,7 @@ inline bool make_tma_ring_plan(const MrlaLightArgs& a, TmaBwdPlan* p) {
   p->S = S;
   p->ncb = (a.C + CB - 1) / CB;
   p->items = p->ncb * a.B;
-  const int slots = p->big ? kNumSMs : 2 * kNumSMs;
+  const int slots = p->big ? kNumSMs : 3 * kNumSMs;
   int grid = p->items < slots ? p->items : slots;
   p->ipc = (p->items + grid - 1) / grid;
   p->grid = (p->items + p->ipc - 1) / p->ipc;
@@ -398,7 +400,7 @@ int light_backward_impl(const MrlaLightArgs& a, cudaStream_t st) {
                      tma_ptr_ok(a.dy, a.bs_dy, es_) && (a.bs_dx * es_) % 4 == 0 && (a.bs_do * es_) % 4 == 0 &&
                      make_tma_bwd_plan(a, &tpb);
   TmaBwdPlan tpr;
-  const bool tma_r = tma_b && make_tma_ring_plan(a, &tpr) && tpr.big;  // small images keep the halo-recompute kernel
+  const bool tma_r = tma_b && make_tma_ring_plan(a, &tpr);
   const int nparts = tma_r ? tpr.maxslots : (tma_b ? tpb.maxslots : pb.grid_y);
   const size_t need = ((size_t)nparts * a.C * 9 + (size_t)a.B * 2 * a.k_size) * sizeof(float);
   if (a.scratch == nullptr || a.scratch_bytes < need) return MRLA_ERR_WORKSPACE;

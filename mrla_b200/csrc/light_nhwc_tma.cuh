@@ -621,8 +621,9 @@ k_light_nhwc_tma_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 // kernel above needs ~210 registers and runs 7).  Per row step: compute V, T for the 4 own columns, store T[t]
 // into ring slot t%4, one consumer-wide named barrier, then dX[t-1] = res*dy + dyc + Σ wv[i][dj]*T[t-i][w-dj+1]
 // from the ring.  Work items are contiguous (cb, b) ranges so dWv stays in registers across samples.
+// BIG: one 480-thread CTA per SM (W = 56 / 28); !BIG: 160-thread CTAs, three per SM (small images)
 template <typename T, int CB, int ACT, bool BIG>
-__global__ void __launch_bounds__(BIG ? 480 : 288, BIG ? 1 : 2)
+__global__ void __launch_bounds__(BIG ? 480 : 160, BIG ? 1 : 3)
 k_light_nhwc_tma_bwd_ring(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy,
                           const __grid_constant__ CUtensorMap tm_o, TmaBwdParams P) {
   constexpr int NP = CB / 2;
