@@ -125,19 +125,21 @@ int launch_tma_sweep(const MrlaLightArgs& a, cudaStream_t st, const TmaPlan& p, 
                      const void* optr, int64_t bs_o, const void* dyptr, int64_t bs_dy, float* mom) {
   CUtensorMap tx, to, tdy;
   if (make_nhwc_tmap(&tx, xptr, a.dtype, a.B, a.C, a.H, a.W, bs_x, p.CB, p.NQ * kCols + 2, p.G)) return MRLA_ERR_UNSUPPORTED;
-  if (make_nhwc_tmap(&to, optr, a.dtype, a.B, a.C, a.H, a.W, bs_o, p.CB, p.NQ * kCols, p.G)) return MRLA_ERR_UNSUPPORTED;
+  if (MODE == 3) to = tx;
+  else if (make_nhwc_tmap(&to, optr, a.dtype, a.B, a.C, a.H, a.W, bs_o, p.CB, p.NQ * kCols, p.G)) return MRLA_ERR_UNSUPPORTED;
   tdy = to;
-  if (MODE == 2 && make_nhwc_tmap(&tdy, dyptr, a.dtype, a.B, a.C, a.H, a.W, bs_dy, p.CB, p.NQ * kCols, p.G))
+  if ((MODE == 2 || MODE == 4) && make_nhwc_tmap(&tdy, dyptr, a.dtype, a.B, a.C, a.H, a.W, bs_dy, p.CB, p.NQ * kCols, p.G))
     return MRLA_ERR_UNSUPPORTED;
   TmaSweepParams P;
   P.B = a.B; P.C = a.C; P.H = a.H; P.W = a.W;
   P.G = p.G; P.S = p.S; P.NQ = p.NQ; P.ncb = p.ncb; P.items = p.items; P.cons_threads = p.cons_threads;
   P.x_bytes = p.x_bytes; P.o_bytes = p.o_bytes; P.stage_bytes = p.stage_bytes;
   P.wv = a.wv; P.mom = mom; P.coef = a.coef; P.y = a.y; P.bs_y = a.bs_y; P.res = a.residual ? 1.f : 0.f;
+  P.wv_part = (MODE == 4) ? mom : nullptr;   // MODE 4 passes the partial buffer through `mom`
   const int threads = 32 + p.cons_threads;
 #define MRLA_TMA_LAUNCH1(CBV, BIGV)                                                                       \
   {                                                                                                       \
-    auto k = k_light_nhwc_tma<T, CBV, ACT, true, MODE, BIGV>;                                             \
+    auto k = k_light_nhwc_tma<T, CBV, ACT, (MODE != 3), MODE, BIGV>;                                      \
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);    \
     if (e != cudaSuccess) return (int)e;                                                                  \
     k<<<p.grid, threads, p.smem, st>>>(tx, to, tdy, P);                                                   \

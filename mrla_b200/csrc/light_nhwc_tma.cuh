@@ -27,9 +27,10 @@ struct TmaSweepParams {
   const float* wv;      // [C,9]
   float* mom;           // MODE 0: [6,B,C] ; MODE 2: gmom [3,B,C]
   const float* coef;    // MODE 1: [3,B,C]
-  void* y;              // MODE 1
+  void* y;              // MODE 1 / 3 / 4 output
   int64_t bs_y;
   float res;
+  float* wv_part;       // MODE 4: [grid/ncb, C, 9] per-CTA dWv partials
 };
 
 // ---------------------------------------------------------------------------- packed helpers
@@ -110,14 +111,15 @@ __device__ __forceinline__ void conv9x4(const float2 (&top)[kWin], const float2 
 
 // ---------------------------------------------------------------------------- the kernel
 // MODE 0: forward moments (Σx ΣV ΣV² [ΣVo Σo Σo²]) ; MODE 1: forward apply (y) ; MODE 2: backward moments (Σdy ΣdyV [Σdyo])
+// MODE 3: MRLA-base F0 — y = dwconv3x3(x) stored into the V-cache slot, plus Σx (no o tile)
 // BIG: one 480-thread CTA per SM (W = 56 / 28); !BIG: <= 288 threads, two CTAs per SM (small images)
 template <typename T, int CB, int ACT, bool HAS_O, int MODE, bool BIG>
 __global__ void __launch_bounds__(BIG ? 480 : 288, BIG ? 1 : 2)
 k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_o,
                  const __grid_constant__ CUtensorMap tm_dy, TmaSweepParams P) {
   constexpr int NP = CB / 2;                                  // channel pairs per block
-  constexpr int NACC = (MODE == 0) ? (HAS_O ? 6 : 3) : (MODE == 2 ? (HAS_O ? 3 : 2) : 0);
-  constexpr bool HAS_DY = (MODE == 2);
+  constexpr int NACC = (MODE == 0) ? (HAS_O ? 6 : 3) : (MODE == 2 ? (HAS_O ? 3 : 2) : (MODE == 3 ? 1 : 0));
+  constexpr bool HAS_DY = (MODE == 2 || MODE == 4);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* empty = full + 16;
@@ -186,6 +188,9 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   uint32_t oa = stages_s + P.x_bytes + tbase;     // address of o row r
   int cur_cb = -1;   // the grid is a multiple of ncb, so a CTA keeps its channel block: weights are loaded once
   float2 w9[9];
+  float2 dwf[MODE == 4 ? 9 : 1];   // MODE 4: dWv accumulators (flipped tap order), kept across all items of the CTA
+#pragma unroll
+  for (int i = 0; i < (MODE == 4 ? 9 : 1); ++i) dwf[i] = f2(0.f, 0.f);
   int red_sel = 0;   // double-buffered reduction scratch: one consumer barrier per image
 
   for (int item = blockIdx.x; item < P.items; item += gridDim.x) {
@@ -195,8 +200,10 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     if (cb != cur_cb) {
       cur_cb = cb;
 #pragma unroll
-      for (int i = 0; i < 9; ++i)
-        w9[i] = chan_ok ? f2(P.wv[(int64_t)c * 9 + i], P.wv[(int64_t)(c + 1) * 9 + i]) : f2(0.f, 0.f);
+      for (int i = 0; i < 9; ++i) {
+        const int wi = (MODE == 4) ? 8 - i : i;   // MODE 4 correlates with the flipped kernel (transposed conv)
+        w9[i] = chan_ok ? f2(P.wv[(int64_t)c * 9 + wi], P.wv[(int64_t)(c + 1) * 9 + wi]) : f2(0.f, 0.f);
+      }
     }
     float2 cA = f2(0.f, 0.f), cL = f2(0.f, 0.f), cD = f2(0.f, 0.f);
     if (MODE == 1 && chan_ok) {
@@ -206,12 +213,13 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       if (HAS_O) cL = *reinterpret_cast<const float2*>(cp + BC);
       cD = *reinterpret_cast<const float2*>(cp + 2 * BC);
     }
+    if (MODE == 4 && chan_ok) cD = *reinterpret_cast<const float2*>(P.coef + (int64_t)b * P.C + c);  // GAP grad / HW
     const float2 res2 = f2(P.res, P.res);
     float2 acc[NACC > 0 ? NACC : 1], accb[NACC > 0 ? NACC : 1];  // even / odd columns: two independent chains
 #pragma unroll
     for (int i = 0; i < (NACC > 0 ? NACC : 1); ++i) { acc[i] = f2(0.f, 0.f); accb[i] = f2(0.f, 0.f); }
     // running pointer to this thread's first output column of the row being produced
-    T* yrow = (MODE == 1) ? static_cast<T*>(P.y) + (int64_t)b * P.bs_y + (int64_t)(q * kCols) * P.C + c : nullptr;
+    T* yrow = (MODE == 1 || MODE == 3 || MODE == 4) ? static_cast<T*>(P.y) + (int64_t)b * P.bs_y + (int64_t)(q * kCols) * P.C + c : nullptr;
     const int64_t y_row_stride = (int64_t)P.W * P.C;
     bool sv[kCols];
 #pragma unroll
@@ -280,6 +288,22 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 A[0] = fadd2(A[0], gv);
                 A[1] = ffma2(gv, v, A[1]);
                 if (HAS_O) A[2] = ffma2(gv, ov, A[2]);
+              } else if (MODE == 3) {
+                A[0] = fadd2(A[0], xc);
+                if (sv[j]) stg_pair<T>(yrow + j * P.C, v);
+              } else if (MODE == 4) {
+                // window = dV_t, ov = x centre, gv = dy:  dX = res*dy + dyc + conv(dV_t, flipped wv) ;
+                // dW'[k] += x * window_k  (k over the flipped tap order; un-flipped when flushed)
+                if (sv[j]) stg_pair<T>(yrow + j * P.C, fadd2(ffma2(res2, gv, cD), v));
+                dwf[0] = ffma2(ov, top[j], dwf[0]);
+                dwf[1] = ffma2(ov, top[j + 1], dwf[1]);
+                dwf[2] = ffma2(ov, top[j + 2], dwf[2]);
+                dwf[3] = ffma2(ov, mid[j], dwf[3]);
+                dwf[4] = ffma2(ov, mid[j + 1], dwf[4]);
+                dwf[5] = ffma2(ov, mid[j + 2], dwf[5]);
+                dwf[6] = ffma2(ov, bot[j], dwf[6]);
+                dwf[7] = ffma2(ov, bot[j + 1], dwf[7]);
+                dwf[8] = ffma2(ov, bot[j + 2], dwf[8]);
               } else {
                 float2 t = ffma2(cA, v, cD);
                 if (HAS_O) t = ffma2(cL, ov, t);
@@ -287,7 +311,7 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 if (sv[j]) stg_pair<T>(yrow + j * P.C, t);
               }
             }
-            if (MODE == 1) yrow += y_row_stride;
+            if (MODE == 1 || MODE == 3 || MODE == 4) yrow += y_row_stride;
             // release the group whose last row was just consumed
             if (rel_stage >= 0) {
               __syncwarp();
@@ -320,6 +344,29 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         }
         const int cc = cb * CB + 2 * pp;
         if (cc < P.C) *reinterpret_cast<float2*>(P.mom + (int64_t)mi * BC + (int64_t)b * P.C + cc) = s;
+      }
+    }
+  }
+  if (MODE == 4) {
+    // one partial per CTA: CTAs with blockIdx = cb (mod ncb) share a channel block -> slot = blockIdx / ncb
+    float2* red = red_base;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) red[((size_t)q * 9 + i) * NP + p] = dwf[i];
+    named_bar_sync(1, P.cons_threads);
+    const int slot = blockIdx.x / P.ncb;
+    for (int idx = ct; idx < 9 * NP; idx += P.cons_threads) {
+      const int kf = idx / NP, pp = idx - kf * NP;
+      float2 s = f2(0.f, 0.f);
+      for (int qq = 0; qq < P.NQ; ++qq) {
+        const float2 v = red[((size_t)qq * 9 + kf) * NP + pp];
+        s.x += v.x;
+        s.y += v.y;
+      }
+      const int cc = cur_cb * CB + 2 * pp;
+      if (cur_cb >= 0 && cc < P.C) {
+        float* dst = P.wv_part + ((int64_t)slot * P.C + cc) * 9 + (8 - kf);
+        dst[0] = s.x;
+        dst[9] = s.y;
       }
     }
   }

@@ -484,7 +484,6 @@ class _BaseTail(torch.autograd.Function):
         _Prof.end("base_bwd", (B, C, H, W, x_c.dtype, layout), ev)
         launch_counter["bwd"] += L.mrla_last_launch_count()
         cache.bwd_started = True
-
         def back(i, g_):
             meta = ctx.param_meta[i]
             return None if meta is None or g_ is None else _like_param(g_, meta)
@@ -508,6 +507,10 @@ def base_tail(x, prev_k, prev_v, wq, wk, wv, gamma=None, beta=None, running_mean
     (reference signature: mrla_base_module.py:54-89 `forward(x, prev_K, prev_V) -> (out, K, V)`)."""
     _require_cuda(x, "x")
     x_c, layout, _ = _canon(x)
+    if layout == _lib.NCHW and out is None and _want_nhwc(x_c):
+        prev_cache = None if (init_cell or prev_k is None) else getattr(prev_k, "_mrla_cache", None)
+        if prev_cache is None or prev_cache.layout == _lib.NHWC:
+            x_c, layout = _ToNHWC.apply(x_c), _lib.NHWC   # promote onto the NHWC fast path (see PROMOTE_NCHW)
     ext_k = ext_v = None
     if init_cell or prev_k is None:
         cache = StageCache(x_c, layout, cap_hint)
@@ -527,10 +530,14 @@ def base_tail(x, prev_k, prev_v, wq, wk, wv, gamma=None, beta=None, running_mean
             ext_k, ext_v = prev_k, prev_v
     t = cache.t + 1
     cache.reserve(t)
-    y, token = _BaseTail.apply(x_c, wq, wk, wv, gamma, beta, ext_k, ext_v, getattr(cache, "token", None),
-                               running_mean, running_var, drop_scale, cache, t, cfg, out)
-    cache.token = token if token.requires_grad else None
+    prev_token = getattr(prev_k, "_mrla_token", None) if (prev_k is not None and ext_k is None) else None
+    y, token = _BaseTail.apply(x_c, wq, wk, wv, gamma, beta, ext_k, ext_v, prev_token, running_mean, running_var,
+                               drop_scale, cache, t, cfg, out)
     cache.t = t
     K, V = cache.K_view(t), cache.V_view(t)
+    # The cache and the ordering token ride on the returned K tensor (K -> cache, K -> token -> autograd node ->
+    # cache).  The cache itself holds no reference back, so nothing forms a cycle and the multi-GB slot buffers are
+    # released as soon as the graph and the K/V views die.
     K._mrla_cache = cache
+    K._mrla_token = token if token.requires_grad else None
     return y, K, V

@@ -140,9 +140,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--json", default=None)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default=None, help="base: only the MRLA-base stage rows")
     args = ap.parse_args()
     bf = torch.bfloat16
     out = {}
+    if args.only == "base":
+        out["A6_base_stage_resnet50_bf16_nhwc_B256"] = [base_case(256, C, H, 16, T, bf) for C, H, T in
+                                                        ((256, 56, 3), (512, 28, 4), (1024, 14, 6), (2048, 7, 3))]
+        print(json.dumps(out["A6_base_stage_resnet50_bf16_nhwc_B256"]), flush=True)
+        if args.json:
+            json.dump(out, open(args.json, "w"), indent=1)
+        return
     out["A4_light_tail_resnet50_bf16_nhwc_B256"] = [light_case(256, C, H, H, 32, bf) for C, H in
                                                     ((256, 56), (512, 28), (1024, 14), (2048, 7))]
     print(json.dumps(out["A4_light_tail_resnet50_bf16_nhwc_B256"]), flush=True)
