@@ -148,17 +148,19 @@ def summarize_prof(records, peak):
     """records: (tag, (B,C,H,W,dtype,layout), ev0, ev1) from mrla_b200.ops._Prof -> per-shape fwd/bwd ms."""
     agg = {}
     for tag, key, e0, e1 in records:
-        B, C, H, W, dt, lay = key
-        agg.setdefault((C, H, B, dt), {"light_fwd": [], "light_bwd": []})[tag].append(e0.elapsed_time(e1))
+        B, C, H, W, dt, lay, folded = key
+        agg.setdefault((C, H, B, dt, folded), {"light_fwd": [], "light_bwd": []})[tag].append(e0.elapsed_time(e1))
     out = {}
     tot_bytes = tot_ms = 0.0
-    for (C, H, B, dt), d in agg.items():
+    for (C, H, B, dt, folded), d in agg.items():
         if not d["light_fwd"] or not d["light_bwd"]:
             continue
         f = sum(d["light_fwd"]) / len(d["light_fwd"])
         b = sum(d["light_bwd"]) / len(d["light_bwd"])
         es = torch.empty((), dtype=dt).element_size()
-        nbytes = 8.0 * B * C * H * H * es
+        # algorithmic bytes per block: plain tail 8N (fwd R x,o W y; bwd R dy,x,o W dx,do); with the bottleneck's
+        # residual add + ReLU folded in 9N (fwd R z,id W x,y; bwd R dy,x,id W dz,d_id)
+        nbytes = (9.0 if folded else 8.0) * B * C * H * H * es
         out[(C, H)] = dict(fwd_ms=f, bwd_ms=b, bytes=nbytes, gbs=nbytes / (f + b) / 1e6, calls=len(d["light_fwd"]))
         n = STAGE_BLOCKS.get((C, H), 0)
         tot_bytes += n * nbytes
@@ -257,6 +259,8 @@ def run_product_arm(args):
     s0.record()
     prefetch(0)
     last_loss = 0.0
+    pending = None  # (pinned host scalar, event): the loss of step i is read on the host while step i+1 runs
+    host_loss = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
     for i in range(K):
         img, lbl, ev = slots[i % 2]
         torch.cuda.current_stream().wait_event(ev)
@@ -264,7 +268,15 @@ def run_product_arm(args):
         if i + 1 < K:
             prefetch(i + 1)
         loss = step(img, lbl)
-        last_loss = float(loss.item())  # D2H read of the step's result
+        host_loss[i % 2].copy_(loss.detach(), non_blocking=True)   # D2H read of this step's result
+        done = torch.cuda.Event()
+        done.record()
+        if pending is not None:
+            pending[1].synchronize()
+            last_loss = float(pending[0])
+        pending = (host_loss[i % 2], done)
+    pending[1].synchronize()
+    last_loss = float(pending[0])
     s1.record()
     barrier()
     ms_e2e = max_over_ranks(s0.elapsed_time(s1))
@@ -289,8 +301,9 @@ def run_product_arm(args):
                 traffic = None
         roof = {"bound": "hbm", "achieved": round(d["gbs"], 1), "peak": peak, "unit": "GB/s",
                 "frac": round(d["gbs"] / peak, 4), "traffic": traffic,
-                "kernel": "MRLA-light tail fwd+bwd kernel group, stage-1 shape (B,256,56,56) bf16 NHWC "
-                          "(sweep1+mid+sweep2 / sweepA+mid+sweepB+finish), algorithmic bytes 8*N*2",
+                "kernel": "MRLA-light block tail fwd+bwd kernel group with the bottleneck's residual add+ReLU folded in, "
+                          "stage-1 shape (B,256,56,56) bf16 NHWC (add_relu+sweep1+mid+sweep2 / sweepA+mid+sweepB+finish); "
+                          "algorithmic bytes 9*N*2 per block (fwd R z,id W x,y; bwd R dy,x,id W dz,d_id)",
                 "peak_kind": peak_kind,
                 "launch_ms": {"fwd": round(d["fwd_ms"], 4), "bwd": round(d["bwd_ms"], 4)},
                 "all_16_tails": {"ms_per_step": round(tot_ms, 3), "alg_GB_per_step": round(tot_bytes / 1e9, 3),

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define MRLA_ABI_VERSION 1
+#define MRLA_ABI_VERSION 2
 
 enum { MRLA_F32 = 0, MRLA_BF16 = 1, MRLA_F16 = 2 };
 enum { MRLA_NCHW = 0, MRLA_NHWC = 1 };
@@ -70,6 +70,11 @@ typedef struct MrlaLightArgs {
   int32_t bn_mode;      /* MRLA_BN_*                                                           */
   int32_t residual;     /* 1: y = x + branch (resnet_mrla_light.py:116); 0: y = branch          */
   int32_t update_running; /* 1: BN train mode also updates running_mean/var in place            */
+  int32_t fuse_relu_bwd;  /* backward only: x was produced as relu(z + o) in front of the tail
+                             (resnet_mrla_light.py:113-114).  Then `dx` receives dz = dx_total*[x>0] and
+                             `dout` receives the TOTAL identity gradient lam*dS + dz, which replaces the
+                             reference's threshold_backward and gradient-accumulation passes.          */
+  int32_t reserved0;
   float eps, momentum;  /* BatchNorm2d eps / momentum                                          */
   int64_t bs_x, bs_o, bs_y, bs_dy, bs_dx, bs_do; /* batch strides (elements)                    */
   /* ---- forward tensors ---- */
@@ -118,6 +123,10 @@ size_t mrla_sizeof_light_args(void);
 
 /* bytes of `scratch` mrla_light_backward needs for this problem. */
 size_t mrla_light_bwd_scratch_bytes(const MrlaLightArgs* a);
+
+/* 1 if mrla_light_backward honours `fuse_relu_bwd` for these arguments (layout / shape / alignment), else 0
+ * (the caller then applies the ReLU mask and the identity-gradient sum itself). */
+int mrla_light_bwd_fuses_relu(const MrlaLightArgs* a);
 
 /* y = residual*x + m_b*( BN( gate(x)*act(dwconv3x3(x)) + lambda*o ) ), plus saved statistics. */
 int mrla_light_forward(const MrlaLightArgs* a, void* stream);
@@ -188,6 +197,9 @@ int mrla_base_backward(const MrlaBaseArgs* a, void* stream);
  * Used to promote NCHW callers onto the TMA (channels_last) kernels; replaces at::contiguous(channels_last). */
 int mrla_nchw_to_nhwc(const void* src, void* dst, int B, int C, int HW, int dtype, int64_t bs_src, int64_t bs_dst,
                       void* stream);
+
+/* x = relu(z + idt) over n contiguous elements (16-byte aligned, n multiple of the 16-byte vector width). */
+int mrla_add_relu(const void* z, const void* idt, void* x, int64_t n, int dtype, void* stream);
 
 /* Number of kernel launches the last forward / backward call on this thread enqueued
  * (bench.py reports it as gpu_launches). */

@@ -11,7 +11,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmrla_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 F32, BF16, F16 = 0, 1, 2
 NCHW, NHWC = 0, 1
@@ -33,7 +33,7 @@ class MrlaLightArgs(ctypes.Structure):
     """Mirror of `struct MrlaLightArgs` (include/mrla_b200.h) — field order must match."""
     _fields_ = (
         [(n, _i32) for n in ("B", "C", "H", "W", "dim_perhead", "k_size", "dtype", "layout", "act", "bn_mode",
-                             "residual", "update_running")]
+                             "residual", "update_running", "fuse_relu_bwd", "reserved0")]
         + [("eps", _f32), ("momentum", _f32)]
         + [(n, _i64) for n in ("bs_x", "bs_o", "bs_y", "bs_dy", "bs_dx", "bs_do")]
         + [(n, _vp) for n in ("x", "o", "y", "wq", "wk", "wv", "lam", "gamma", "beta", "running_mean", "running_var",
@@ -62,8 +62,8 @@ _lock = threading.Lock()
 
 EXPORTS = (
     "mrla_abi_version", "mrla_build_info", "mrla_last_launch_count", "mrla_sizeof_light_args",
-    "mrla_light_bwd_scratch_bytes", "mrla_light_forward", "mrla_light_backward",
-    "mrla_nchw_to_nhwc", "mrla_sizeof_base_args", "mrla_base_bwd_scratch_bytes", "mrla_base_forward", "mrla_base_backward",
+    "mrla_light_bwd_scratch_bytes", "mrla_light_bwd_fuses_relu", "mrla_light_forward", "mrla_light_backward",
+    "mrla_nchw_to_nhwc", "mrla_add_relu", "mrla_sizeof_base_args", "mrla_base_bwd_scratch_bytes", "mrla_base_forward", "mrla_base_backward",
 )
 
 
@@ -92,6 +92,11 @@ def lib() -> ctypes.CDLL:
         L.mrla_nchw_to_nhwc.restype = ctypes.c_int
         L.mrla_nchw_to_nhwc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]
+        L.mrla_light_bwd_fuses_relu.restype = ctypes.c_int
+        L.mrla_light_bwd_fuses_relu.argtypes = [ctypes.POINTER(MrlaLightArgs)]
+        L.mrla_add_relu.restype = ctypes.c_int
+        L.mrla_add_relu.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+                                    ctypes.c_void_p]
         L.mrla_sizeof_base_args.restype = ctypes.c_size_t
         if L.mrla_sizeof_base_args() != ctypes.sizeof(MrlaBaseArgs):
             raise RuntimeError("MrlaBaseArgs layout mismatch between _lib.py and include/mrla_b200.h")

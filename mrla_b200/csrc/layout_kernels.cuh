@@ -41,4 +41,20 @@ __global__ void __launch_bounds__(256) k_nchw_to_nhwc(const T* __restrict__ src,
   }
 }
 
+// x = relu(z + id): the residual add + ReLU in front of the MRLA tail (resnet_mrla_light.py:113-114), one
+// vectorised pass (R2 W1) instead of the reference's in-place add (R2 W1) followed by relu_ (R1 W1).
+template <typename T>
+__global__ void __launch_bounds__(256) k_add_relu(const T* __restrict__ z, const T* __restrict__ idt, T* __restrict__ x,
+                                                  int64_t n_vec) {
+  constexpr int V = 16 / sizeof(T);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    float a[V], b[V];
+    ld_vec<T, V>(z + i * V, a);
+    ld_vec<T, V>(idt + i * V, b);
+#pragma unroll
+    for (int k = 0; k < V; ++k) a[k] = fmaxf(a[k] + b[k], 0.f);
+    st_vec<T, V>(x + i * V, a);
+  }
+}
+
 }  // namespace mrla

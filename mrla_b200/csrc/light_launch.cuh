@@ -306,12 +306,16 @@ int launch_tma_bwd_ring(const MrlaLightArgs& a, cudaStream_t st, const TmaBwdPla
   P.wv = a.wv; P.lam = a.lam; P.bcoef = a.bcoef; P.dx = a.dx; P.dout = a.dout; P.bs_dx = a.bs_dx; P.bs_do = a.bs_do;
   P.res = a.residual ? 1.f : 0.f; P.wv_part = wv_part;
   const int threads = 32 + p.cons_threads;
-#define MRLA_TMA_LAUNCH1(CBV, BIGV)                                                                       \
+#define MRLA_TMA_LAUNCH2(CBV, BIGV, FUSEV)                                                                \
   {                                                                                                       \
-    auto k = k_light_nhwc_tma_bwd_ring<T, CBV, ACT, BIGV>;                                                \
+    auto k = k_light_nhwc_tma_bwd_ring<T, CBV, ACT, BIGV, FUSEV>;                                         \
     e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);                \
     if (e != cudaSuccess) return (int)e;                                                                  \
     k<<<p.grid, threads, p.smem, st>>>(tx, tdy, to, P);                                                   \
+  }
+#define MRLA_TMA_LAUNCH1(CBV, BIGV)                                                                       \
+  {                                                                                                       \
+    if (a.fuse_relu_bwd) MRLA_TMA_LAUNCH2(CBV, BIGV, true) else MRLA_TMA_LAUNCH2(CBV, BIGV, false)        \
   }
 #define MRLA_TMA_LAUNCH(CBV)                                                                              \
   {                                                                                                       \
@@ -325,8 +329,18 @@ int launch_tma_bwd_ring(const MrlaLightArgs& a, cudaStream_t st, const TmaBwdPla
   }
 #undef MRLA_TMA_LAUNCH
 #undef MRLA_TMA_LAUNCH1
+#undef MRLA_TMA_LAUNCH2
   MRLA_CHECK_LAUNCH();
   return MRLA_OK;
+}
+
+// does the backward of these arguments run the kernel that implements fuse_relu_bwd?
+inline bool light_bwd_can_fuse_relu(const MrlaLightArgs& a) {
+  if (a.layout != MRLA_NHWC || a.o == nullptr || a.act != MRLA_ACT_NONE) return false;
+  const int es = a.dtype == MRLA_F32 ? 4 : 2;
+  TmaBwdPlan tpb, tpr;
+  return tma_ptr_ok(a.x, a.bs_x, es) && tma_ptr_ok(a.o, a.bs_o, es) && tma_ptr_ok(a.dy, a.bs_dy, es) &&
+         (a.bs_dx * es) % 4 == 0 && (a.bs_do * es) % 4 == 0 && make_tma_bwd_plan(a, &tpb) && make_tma_ring_plan(a, &tpr);
 }
 
 // ------------------------------------------------------------------------------------ forward
@@ -403,6 +417,7 @@ int light_backward_impl(const MrlaLightArgs& a, cudaStream_t st) {
                      make_tma_bwd_plan(a, &tpb);
   TmaBwdPlan tpr;
   const bool tma_r = tma_b && make_tma_ring_plan(a, &tpr);
+  if (a.fuse_relu_bwd && !tma_r) return MRLA_ERR_UNSUPPORTED;   // callers ask mrla_light_bwd_fuses_relu() first
   const int nparts = tma_r ? tpr.maxslots : (tma_b ? tpb.maxslots : pb.grid_y);
   const size_t need = ((size_t)nparts * a.C * 9 + (size_t)a.B * 2 * a.k_size) * sizeof(float);
   if (a.scratch == nullptr || a.scratch_bytes < need) return MRLA_ERR_WORKSPACE;

@@ -66,6 +66,42 @@ template <> __device__ __forceinline__ void stg_pair<float>(float* p, float2 v) 
   *reinterpret_cast<float2*>(p) = v;
 }
 
+template <typename T> __device__ __forceinline__ float2 ldg_pair(const T* p);
+template <> __device__ __forceinline__ float2 ldg_pair<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint32_t u = *reinterpret_cast<const volatile uint32_t*>(p);
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+template <> __device__ __forceinline__ float2 ldg_pair<__half>(const __half* p) {
+  uint32_t u = *reinterpret_cast<const volatile uint32_t*>(p);
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+template <> __device__ __forceinline__ float2 ldg_pair<float>(const float* p) {
+  const volatile float* q = p;
+  return make_float2(q[0], q[1]);
+}
+
+// an output pair in the precision it will be stored with (one 32-bit register for bf16 / fp16)
+template <typename T> struct RawPair { typedef uint32_t type; };
+template <> struct RawPair<float> { typedef float2 type; };
+template <typename T> __device__ __forceinline__ typename RawPair<T>::type pack_pair(float2 v);
+template <> __device__ __forceinline__ uint32_t pack_pair<__nv_bfloat16>(float2 v) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack_pair<__half>(float2 v) {
+  const __half2 h = __floats2half2_rn(v.x, v.y);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ float2 pack_pair<float>(float2 v) { return v; }
+template <typename T> __device__ __forceinline__ float2 unpack_pair(typename RawPair<T>::type r);
+template <> __device__ __forceinline__ float2 unpack_pair<__nv_bfloat16>(uint32_t u) {
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+template <> __device__ __forceinline__ float2 unpack_pair<__half>(uint32_t u) {
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+template <> __device__ __forceinline__ float2 unpack_pair<float>(float2 v) { return v; }
+
 template <int ACT> __device__ __forceinline__ float2 act2(float2 u) {
   if (ACT == 1) return make_float2(act_fwd<1>(u.x), act_fwd<1>(u.y));
   return u;
@@ -669,7 +705,9 @@ k_light_nhwc_tma_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 // into ring slot t%4, one consumer-wide named barrier, then dX[t-1] = res*dy + dyc + Σ wv[i][dj]*T[t-i][w-dj+1]
 // from the ring.  Work items are contiguous (cb, b) ranges so dWv stays in registers across samples.
 // BIG: one 480-thread CTA per SM (W = 56 / 28); !BIG: 160-thread CTAs, three per SM (small images)
-template <typename T, int CB, int ACT, bool BIG>
+// FUSE: x = relu(z + o) was formed in front of the tail; the epilogue writes dz = dx_total*[x>0] into dx and the
+//       total identity gradient lam*dS + dz into dout (no separate threshold_backward / grad-accumulation pass).
+template <typename T, int CB, int ACT, bool BIG, bool FUSE>
 __global__ void __launch_bounds__(BIG ? 480 : 160, BIG ? 1 : 3)
 k_light_nhwc_tma_bwd_ring(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy,
                           const __grid_constant__ CUtensorMap tm_o, TmaBwdParams P) {
@@ -827,6 +865,11 @@ k_light_nhwc_tma_bwd_ring(const __grid_constant__ CUtensorMap tm_x, const __grid
     for (int k = 0; k < kWin; ++k) xw[2][k] = f2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < kCols; ++j) dyprev[j] = f2(0.f, 0.f);
+    // FUSE: lam*dS of the previous T row, kept in storage precision (one register per pair) until its dX row is
+    // emitted one step later
+    typename RawPair<T>::type doprev[FUSE ? kCols : 1], docur[FUSE ? kCols : 1];
+#pragma unroll
+    for (int j = 0; j < (FUSE ? kCols : 1); ++j) doprev[j] = pack_pair<T>(f2(0.f, 0.f));
     bool sv[kCols];
 #pragma unroll
     for (int j = 0; j < kCols; ++j) sv[j] = chan_ok && cvalid[j];
@@ -861,6 +904,8 @@ k_light_nhwc_tma_bwd_ring(const __grid_constant__ CUtensorMap tm_x, const __grid
           float2 dycur[kCols];
 #pragma unroll
           for (int j = 0; j < kCols; ++j) dycur[j] = f2(0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < (FUSE ? kCols : 1); ++j) docur[j] = pack_pair<T>(f2(0.f, 0.f));
           // ---- T row t = r-1 ----
           if (r >= 1 && r <= P.H) {
             const int t = r - 1;
@@ -884,7 +929,8 @@ k_light_nhwc_tma_bwd_ring(const __grid_constant__ CUtensorMap tm_x, const __grid
               if (ragged && !cvalid[j]) tt = f2(0.f, 0.f);
               dycur[j] = gy;
               asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(rslot + j * TS), "f"(tt.x), "f"(tt.y) : "memory");
-              if (sv[j]) stg_pair<T>(dop + j * P.C, fmul2(lm, ds));
+              if (FUSE) docur[j] = pack_pair<T>(fmul2(lm, ds));
+              else if (sv[j]) stg_pair<T>(dop + j * P.C, fmul2(lm, ds));
               dw[0] = ffma2(tt, top[j], dw[0]);
               dw[1] = ffma2(tt, top[j + 1], dw[1]);
               dw[2] = ffma2(tt, top[j + 2], dw[2]);
@@ -895,7 +941,7 @@ k_light_nhwc_tma_bwd_ring(const __grid_constant__ CUtensorMap tm_x, const __grid
               dw[7] = ffma2(tt, bot[j + 1], dw[7]);
               dw[8] = ffma2(tt, bot[j + 2], dw[8]);
             }
-            dop += row_stride;
+            if (!FUSE) dop += row_stride;
             if (rel_stage >= 0) {
               __syncwarp();
               if (lane == 0) mbar_arrive(&empty[rel_stage]);
@@ -927,13 +973,29 @@ k_light_nhwc_tma_bwd_ring(const __grid_constant__ CUtensorMap tm_x, const __grid
                 }
               }
             }
+            if (FUSE) {
+              const float2(&xrow)[kWin] = xw[(i + 1) % 3];   // x row h = r-2
 #pragma unroll
-            for (int j = 0; j < kCols; ++j)
-              if (sv[j]) stg_pair<T>(dxp + j * P.C, acc[j]);
+              for (int j = 0; j < kCols; ++j) {
+                const float2 xc = xrow[j + 1];
+                const float2 dz = f2(xc.x > 0.f ? acc[j].x : 0.f, xc.y > 0.f ? acc[j].y : 0.f);
+                if (sv[j]) {
+                  stg_pair<T>(dxp + j * P.C, dz);
+                  stg_pair<T>(dop + j * P.C, fadd2(unpack_pair<T>(doprev[j]), dz));   // total identity gradient
+                }
+              }
+              dop += row_stride;
+            } else {
+#pragma unroll
+              for (int j = 0; j < kCols; ++j)
+                if (sv[j]) stg_pair<T>(dxp + j * P.C, acc[j]);
+            }
             dxp += row_stride;
           }
 #pragma unroll
           for (int j = 0; j < kCols; ++j) dyprev[j] = dycur[j];
+#pragma unroll
+          for (int j = 0; j < (FUSE ? kCols : 1); ++j) doprev[j] = docur[j];
         }
       }
     }

@@ -94,6 +94,11 @@ size_t mrla_light_bwd_scratch_bytes(const MrlaLightArgs* a) {
   return light_bwd_scratch_floats(*a) * sizeof(float);
 }
 
+int mrla_light_bwd_fuses_relu(const MrlaLightArgs* a) {
+  if (a == nullptr) return 0;
+  return light_bwd_can_fuse_relu(*a) ? 1 : 0;
+}
+
 int mrla_light_forward(const MrlaLightArgs* a, void* stream) {
   g_launch_count = 0;
   int rc = check_common(a, false);
@@ -134,6 +139,27 @@ int mrla_nchw_to_nhwc(const void* src, void* dst, int B, int C, int HW, int dtyp
     k_nchw_to_nhwc<float><<<grid, 256, 0, st>>>(static_cast<const float*>(src), static_cast<float*>(dst), C, HW, bs_src, bs_dst);
   else
     k_nchw_to_nhwc<uint16_t><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(src), static_cast<uint16_t*>(dst), C, HW, bs_src, bs_dst);
+  MRLA_CHECK_LAUNCH();
+  return MRLA_OK;
+}
+
+int mrla_add_relu(const void* z, const void* idt, void* x, int64_t n, int dtype, void* stream) {
+  g_launch_count = 0;
+  if (!z || !idt || !x) return MRLA_ERR_NULL;
+  if (n < 1) return MRLA_ERR_SHAPE;
+  if (dtype < MRLA_F32 || dtype > MRLA_F16) return MRLA_ERR_UNSUPPORTED;
+  const int64_t v = 16 / (int64_t)esize(dtype);
+  if (n % v || ((uintptr_t)z % 16) || ((uintptr_t)idt % 16) || ((uintptr_t)x % 16)) return MRLA_ERR_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t nv = n / v;
+  int64_t blocks = (nv + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (dtype == MRLA_F32)
+    k_add_relu<float><<<(int)blocks, 256, 0, st>>>(static_cast<const float*>(z), static_cast<const float*>(idt), static_cast<float*>(x), nv);
+  else if (dtype == MRLA_BF16)
+    k_add_relu<__nv_bfloat16><<<(int)blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(z), static_cast<const __nv_bfloat16*>(idt), static_cast<__nv_bfloat16*>(x), nv);
+  else
+    k_add_relu<__half><<<(int)blocks, 256, 0, st>>>(static_cast<const __half*>(z), static_cast<const __half*>(idt), static_cast<__half*>(x), nv);
   MRLA_CHECK_LAUNCH();
   return MRLA_OK;
 }

@@ -32,6 +32,7 @@ class LightCfg(NamedTuple):
     update_running: bool = True
     eps: float = 1e-5
     momentum: float = 0.1
+    fuse_add_relu: bool = False   # first tensor is z: x = relu(z + o) is formed inside the op (bottleneck :113-114)
 
 
 # --------------------------------------------------------------------------------- layout helpers
@@ -163,6 +164,20 @@ class _ToNHWC(torch.autograd.Function):
         return g
 
 
+def _add_relu(z: torch.Tensor, o: torch.Tensor, layout: int, bs_z: int, bs_o: int) -> torch.Tensor:
+    """x = relu(z + o) in one pass (mrla_add_relu); both operands dense in `layout`."""
+    B, C, H, W = z.shape
+    n = C * H * W
+    vec = 16 // z.element_size()
+    if bs_z == n and bs_o == n and (B * n) % vec == 0 and z.data_ptr() % 16 == 0 and o.data_ptr() % 16 == 0:
+        x = _empty_like_layout(z, layout)
+        _lib.check(_lib.lib().mrla_add_relu(z.data_ptr(), o.data_ptr(), x.data_ptr(), B * n, _DTYPES[z.dtype], _stream()),
+                   "mrla_add_relu")
+        return x
+    x = torch.relu(z + o)
+    return _canon(x, layout)[0]
+
+
 def _want_nhwc(x: torch.Tensor) -> bool:
     B, C, H, W = x.shape
     return PROMOTE_NCHW and x.numel() >= PROMOTE_MIN_ELEMS and C % 8 == 0 and W <= 56 and H * W > 1
@@ -191,6 +206,12 @@ class _LightTail(torch.autograd.Function):
                 o_c, _, bs_o = _canon(o, layout)
         else:
             o_c, bs_o = None, 0
+        ev = _Prof.begin()
+        if cfg.fuse_add_relu:
+            if not has_o:
+                raise RuntimeError("mrla_b200: fuse_add_relu needs o_prev (x = relu(z + o_prev))")
+            x_c, bs_x = _add_relu(x_c, o_c, layout, bs_x, bs_o), C * H * W
+            launch_counter["fwd"] += 1
         if out is not None:
             lay = _layout_of(out)
             if lay is None or lay[0] != layout or out.dtype != x.dtype or out.shape != x.shape:
@@ -224,9 +245,8 @@ class _LightTail(torch.autograd.Function):
         a.gamma, a.beta, a.running_mean, a.running_var = _ptr(ga32), _ptr(be32), _ptr(rm), _ptr(rv)
         a.drop_scale = _ptr(ds32)
         a.mom, a.gate, a.mean, a.rstd, a.coef = _ptr(mom), _ptr(gate), _ptr(stats[0]), _ptr(stats[1]), _ptr(coef)
-        ev = _Prof.begin()
         _lib.check(L.mrla_light_forward(ctypes.byref(a), _stream()), "mrla_light_forward")
-        _Prof.end("light_fwd", (B, C, H, W, x.dtype, layout), ev)
+        _Prof.end("light_fwd", (B, C, H, W, x.dtype, layout, bool(cfg.fuse_add_relu)), ev)
         launch_counter["fwd"] += L.mrla_last_launch_count()
         if rm is not None and rm is not running_mean and cfg.bn_mode == _lib.BN_TRAIN and cfg.update_running:
             running_mean.copy_(rm)
@@ -284,13 +304,19 @@ class _LightTail(torch.autograd.Function):
         a.dgamma = _ptr(dch[1]) if has_bn else None
         a.dbeta = _ptr(dch[2]) if has_bn else None
         a.gmom, a.bcoef = _ptr(gmom), _ptr(bcoef)
+        fused_epilogue = bool(cfg.fuse_add_relu and L.mrla_light_bwd_fuses_relu(ctypes.byref(a)))
+        a.fuse_relu_bwd = int(fused_epilogue)
         nbytes = L.mrla_light_bwd_scratch_bytes(ctypes.byref(a))
         scratch = torch.empty((max(nbytes, 4) + 3) // 4, **f32)
         a.scratch, a.scratch_bytes = _ptr(scratch), scratch.numel() * 4
         ev = _Prof.begin()
         _lib.check(L.mrla_light_backward(ctypes.byref(a), _stream()), "mrla_light_backward")
-        _Prof.end("light_bwd", (B, C, H, W, x_c.dtype, layout), ev)
+        _Prof.end("light_bwd", (B, C, H, W, x_c.dtype, layout, bool(cfg.fuse_add_relu)), ev)
         launch_counter["bwd"] += L.mrla_last_launch_count()
+        if cfg.fuse_add_relu and not fused_epilogue:
+            # shapes the ring kernel does not cover: ReLU mask + identity-gradient sum with library ops
+            dx = dx * (x_c > 0).to(dx.dtype)
+            dout = dout + dx
 
         def back(i, g):
             meta = ctx.param_meta[i]

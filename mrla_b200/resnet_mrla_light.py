@@ -42,9 +42,15 @@ def _bn_effective_momentum(bn: nn.BatchNorm2d) -> float:
     return bn.momentum
 
 
-def mrla_light_block_tail(out, identity, mrla: mrla_module, bn: nn.BatchNorm2d, drop_path: nn.Module):
+def mrla_light_block_tail(out, identity, mrla: mrla_module, bn: nn.BatchNorm2d, drop_path: nn.Module,
+                          pre_add_relu: bool = False):
     """Fused `out + drop_path(bn(mrla(out, identity)))` (reference :116; mmdet variant
-    mmdetection/mmdet/models/backbones/resnet_mrlal.py:116 = eval-mode BN, no DropPath)."""
+    mmdetection/mmdet/models/backbones/resnet_mrlal.py:116 = eval-mode BN, no DropPath).
+
+    `pre_add_relu=True`: `out` is the pre-activation bn3 output and the residual add + ReLU of the bottleneck
+    (`out += identity; out = relu(out)`, reference :113-114) is folded into the op: one pass forms
+    x = relu(out + identity), and the backward epilogue of sweep B emits d(out) = dx*[x>0] and the TOTAL
+    identity gradient directly (no threshold_backward / gradient-accumulation passes)."""
     layer = mrla.mrla
     use_batch_stats = bn.training or bn.running_mean is None
     if use_batch_stats:
@@ -54,7 +60,8 @@ def mrla_light_block_tail(out, identity, mrla: mrla_module, bn: nn.BatchNorm2d, 
         mode, momentum = _lib.BN_EVAL, 0.0
     update = bn.training and bn.track_running_stats and bn.running_mean is not None
     scale = drop_path.scale(out) if isinstance(drop_path, DropPath) else None
-    cfg = layer.cfg(bn_mode=mode, residual=True, update_running=update, eps=bn.eps, momentum=momentum)
+    cfg = layer.cfg(bn_mode=mode, residual=True, update_running=update, eps=bn.eps, momentum=momentum,
+                    fuse_add_relu=pre_add_relu)
     y = light_tail(out, identity, layer.Wq.weight, layer.Wk.weight, layer.Wv.weight, mrla.lambda_t,
                    bn.weight, bn.bias, bn.running_mean, bn.running_var, scale, cfg=cfg)
     if update:
@@ -100,8 +107,8 @@ class MRLA_Bottleneck(nn.Module):
         out = self.relu(self.bn1(self.conv1(x)))
         out = self.relu(self.bn2(self.conv2(out)))
         out = self.bn3(self.conv3(out))
-        out = self.relu(out + identity)
-        return mrla_light_block_tail(out, identity, self.mrla, self.bn_mrla, self.drop_path)
+        # `out += identity; relu` (reference :113-114) is folded into the tail op
+        return mrla_light_block_tail(out, identity, self.mrla, self.bn_mrla, self.drop_path, pre_add_relu=True)
 
 
 class ResNet_mrlal(nn.Module):

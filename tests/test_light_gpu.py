@@ -207,3 +207,48 @@ def test_module_and_block_tail_match_golden(cuda_device):
     ref = O.light_module(g["x"], g["o"], P["mrla.Wq.weight"], P["mrla.Wk.weight"], P["mrla.Wv.weight"], P["lambda_t"],
                          g["C"] // g["d"])
     assert rel_err(mod(x.detach(), o.detach()), ref) < 1e-5
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("shape,dtype", [((4, 64, 7, 7), torch.float32), ((3, 256, 9, 13), torch.float32),
+                                         ((32, 256, 56, 56), torch.bfloat16), ((32, 1024, 14, 14), torch.float32),
+                                         ((64, 2048, 7, 7), torch.bfloat16)])
+def test_light_tail_with_folded_add_relu(shape, dtype, layout, cuda_device):
+    """`pre_add_relu`: x = relu(z + identity) formed inside the op (resnet_mrla_light.py:113-114 folded in) —
+    output and the gradients w.r.t. z and identity (TOTAL, incl. the path through x) match the oracle applied to
+    relu(z + identity).  Covers the fused sweep-B epilogue (TMA shapes) and the library-op fallback (small shapes)."""
+    from mrla_b200 import _lib
+    from mrla_b200.modules.mrla_light_module import eca_kernel_size
+    from mrla_b200.ops import LightCfg, light_tail
+    from oracle import mrla_oracle as O
+    dev = cuda_device
+    B, C, H, W = shape
+    torch.manual_seed(B * 7 + C)
+    d, k = 32, eca_kernel_size(C)
+    z = _to(torch.randn(B, C, H, W, device=dev), dtype, layout, dev)
+    idt = _to(torch.randn(B, C, H, W, device=dev), dtype, layout, dev)
+    dy = _to(torch.randn(B, C, H, W, device=dev), dtype, layout, dev)
+    P = dict(wq=torch.randn(k, device=dev) * 0.5, wk=torch.randn(k, device=dev) * 0.5,
+             wv=torch.randn(C, 1, 3, 3, device=dev) * 0.4, lam=torch.randn(C, 1, 1, device=dev),
+             gamma=1 + 0.3 * torch.randn(C, device=dev), beta=0.2 * torch.randn(C, device=dev))
+    for v in P.values():
+        v.requires_grad_()
+    zg, ig = z.clone().requires_grad_(), idt.clone().requires_grad_()
+    cfg = LightCfg(dim_perhead=d, k_size=k, bn_mode=_lib.BN_TRAIN, residual=True, fuse_add_relu=True)
+    y = light_tail(zg, ig, P["wq"], P["wk"], P["wv"], P["lam"], P["gamma"], P["beta"], torch.zeros(C, device=dev),
+                   torch.ones(C, device=dev), None, cfg=cfg)
+    y.backward(dy)
+    zd, idd = z.double().requires_grad_(), idt.double().requires_grad_()
+    Pd = {n: v.detach().double().requires_grad_() for n, v in P.items()}
+    xd = torch.relu(zd + idd)
+    if dtype != torch.float32:
+        xd = xd + (xd.detach().to(dtype).double() - xd.detach())  # the op stores x in `dtype`: same rounding, unit gradient
+    yr, _, _ = O.light_tail(xd, idd, Pd["wq"], Pd["wk"], Pd["wv"], Pd["lam"], C // d, Pd["gamma"], Pd["beta"],
+                            torch.zeros(C, dtype=torch.float64, device=dev), torch.ones(C, dtype=torch.float64, device=dev))
+    yr.backward(dy.double())
+    tol = TOL[dtype]
+    assert rel_err(y, yr) < tol
+    assert rel_err(zg.grad, zd.grad) < tol
+    assert rel_err(ig.grad, idd.grad) < tol
+    for n in P:
+        assert rel_err(P[n].grad, Pd[n].grad) < 2 * tol, n
