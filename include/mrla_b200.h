@@ -111,6 +111,10 @@ typedef struct MrlaLightArgs {
   float* bcoef;    /* [7,B,C] */
   float* scratch;  /* partial reductions; size from mrla_light_bwd_scratch_bytes() */
   size_t scratch_bytes;
+  /* ---- optional producer fold (forward only) ---- */
+  const void* z;   /* if non-NULL: pre-activation; forward first forms x = relu(z + o) (resnet_mrla_light.py:113-114)
+                      and WRITES it to the buffer `x` points to (which the caller keeps for backward)            */
+  int64_t bs_z;    /* batch stride of z (elements)                                                               */
 } MrlaLightArgs;
 
 int mrla_abi_version(void);

@@ -39,7 +39,7 @@ class MrlaLightArgs(ctypes.Structure):
         + [(n, _vp) for n in ("x", "o", "y", "wq", "wk", "wv", "lam", "gamma", "beta", "running_mean", "running_var",
                               "drop_scale", "mom", "gate", "mean", "rstd", "coef", "dy", "dx", "dout", "dwq", "dwk",
                               "dwv", "dlam", "dgamma", "dbeta", "gmom", "bcoef", "scratch")]
-        + [("scratch_bytes", ctypes.c_size_t)]
+        + [("scratch_bytes", ctypes.c_size_t), ("z", _vp), ("bs_z", _i64)]
     )
 
 

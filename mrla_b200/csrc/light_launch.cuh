@@ -4,6 +4,7 @@
 #include "light_mid.cuh"
 #include "light_sweeps.cuh"
 #include "light_nhwc_tma.cuh"
+#include "layout_kernels.cuh"
 
 namespace mrla {
 
@@ -78,7 +79,7 @@ struct TmaPlan {
 };
 
 // ntiles = number of [CB,W,G] tiles per stage besides the x tile (o and/or dy); nacc = float2 accumulators/thread
-inline bool make_tma_plan(const MrlaLightArgs& a, int ntiles, int nacc, TmaPlan* p) {
+inline bool make_tma_plan(const MrlaLightArgs& a, int ntiles, int nacc, TmaPlan* p, bool ohalo = false) {
   if (a.layout != MRLA_NHWC || a.C % 8 || a.W > 56) return false;
   const int es = a.dtype == MRLA_F32 ? 4 : 2;
   const int NQ = (a.W + kCols - 1) / kCols;
@@ -89,7 +90,8 @@ inline bool make_tma_plan(const MrlaLightArgs& a, int ntiles, int nacc, TmaPlan*
     if (NQ * 32 <= 448) CB = 64; else return false;
   }
   if (a.act == MRLA_ACT_GELU && CB == 256) CB = 128;
-  const uint32_t xrow = (uint32_t)(NQ * kCols + 2) * CB * es, orow = (uint32_t)(NQ * kCols) * CB * es;
+  const uint32_t xrow = (uint32_t)(NQ * kCols + 2) * CB * es;
+  const uint32_t orow = ohalo ? xrow : (uint32_t)(NQ * kCols) * CB * es;   // MODE 5: the o tile carries halo columns
   p->cons_threads = NQ * (CB / 2);
   p->big = p->cons_threads > 256;
   const size_t budget = (p->big ? 200 : 100) * 1024;   // !big: two CTAs share one SM
@@ -126,7 +128,8 @@ int launch_tma_sweep(const MrlaLightArgs& a, cudaStream_t st, const TmaPlan& p, 
   CUtensorMap tx, to, tdy;
   if (make_nhwc_tmap(&tx, xptr, a.dtype, a.B, a.C, a.H, a.W, bs_x, p.CB, p.NQ * kCols + 2, p.G)) return MRLA_ERR_UNSUPPORTED;
   if (MODE == 3) to = tx;
-  else if (make_nhwc_tmap(&to, optr, a.dtype, a.B, a.C, a.H, a.W, bs_o, p.CB, p.NQ * kCols, p.G)) return MRLA_ERR_UNSUPPORTED;
+  else if (make_nhwc_tmap(&to, optr, a.dtype, a.B, a.C, a.H, a.W, bs_o, p.CB, p.NQ * kCols + (MODE == 5 ? 2 : 0), p.G))
+    return MRLA_ERR_UNSUPPORTED;
   tdy = to;
   if ((MODE == 2 || MODE == 4) && make_nhwc_tmap(&tdy, dyptr, a.dtype, a.B, a.C, a.H, a.W, bs_dy, p.CB, p.NQ * kCols, p.G))
     return MRLA_ERR_UNSUPPORTED;
@@ -356,9 +359,33 @@ int light_forward_impl(const MrlaLightArgs& a, cudaStream_t st) {
   const T* o = static_cast<const T*>(a.o);
   T* y = static_cast<T*>(a.y);
   const int es = a.dtype == MRLA_F32 ? 4 : 2;
-  TmaPlan tp1, tp2;
+  TmaPlan tp1, tp2, tp5;
   const bool tma_ok = LAYOUT == MRLA_NHWC && HAS_O && tma_ptr_ok(a.x, a.bs_x, es) && tma_ptr_ok(a.o, a.bs_o, es) &&
                       (a.bs_y * es) % 4 == 0 && make_tma_plan(a, 1, 6, &tp1) && make_tma_plan(a, 1, 0, &tp2);
+  // optional producer fold: x = relu(z + o)
+  bool x_ready = (a.z == nullptr);
+  if (!x_ready && !HAS_O) return MRLA_ERR_NULL;
+  if (!x_ready && tma_ok && full && ACT == 0 && tma_ptr_ok(a.z, a.bs_z, es) && make_tma_plan(a, 1, 6, &tp5, true)) {
+    // sweep 1 forms and stores x itself (MODE 5): no separate add+relu pass
+    MrlaLightArgs a5 = a;
+    a5.y = const_cast<void*>(a.x);
+    a5.bs_y = a.bs_x;
+    rc = launch_tma_sweep<T, 0, 5>(a5, st, tp5, a.z, a.bs_z, a.o, a.bs_o, nullptr, 0, a.mom);
+    if (rc) return rc;
+    x_ready = true;
+  } else {
+    if (!x_ready) {
+      const int64_t n = (int64_t)a.C * a.H * a.W;
+      const int64_t v = 16 / es;
+      if (a.bs_z != n || a.bs_o != n || a.bs_x != n || (a.B * n) % v || ((uintptr_t)a.z % 16) || ((uintptr_t)a.o % 16) ||
+          ((uintptr_t)a.x % 16))
+        return MRLA_ERR_ALIGN;
+      const int64_t nv = a.B * n / v;
+      int64_t blocks = (nv + 255) / 256;
+      if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+      k_add_relu<T><<<(int)blocks, 256, 0, st>>>(static_cast<const T*>(a.z), o, const_cast<T*>(x), nv);
+      MRLA_CHECK_LAUNCH();
+    }
   // sweep 1
   if (tma_ok && full) {
     rc = launch_tma_sweep<T, ACT, 0>(a, st, tp1, a.x, a.bs_x, a.o, a.bs_o, nullptr, 0, a.mom);
@@ -377,6 +404,7 @@ int light_forward_impl(const MrlaLightArgs& a, cudaStream_t st) {
     }
     MRLA_CHECK_LAUNCH();
   }
+  }  // sweep 1 (skipped when MODE 5 produced the moments together with x)
   // mid
   MidShape ms = mid_shape(a, full);
   {

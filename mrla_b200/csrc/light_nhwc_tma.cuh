@@ -148,13 +148,15 @@ __device__ __forceinline__ void conv9x4(const float2 (&top)[kWin], const float2 
 // ---------------------------------------------------------------------------- the kernel
 // MODE 0: forward moments (Σx ΣV ΣV² [ΣVo Σo Σo²]) ; MODE 1: forward apply (y) ; MODE 2: backward moments (Σdy ΣdyV [Σdyo])
 // MODE 3: MRLA-base F0 — y = dwconv3x3(x) stored into the V-cache slot, plus Σx (no o tile)
+// MODE 4: MRLA-base B4 — window tile = dV_t: dX and dWv ; MODE 5: MODE 0 with x = relu(z + o) formed (and stored) here
 // BIG: one 480-thread CTA per SM (W = 56 / 28); !BIG: <= 288 threads, two CTAs per SM (small images)
 template <typename T, int CB, int ACT, bool HAS_O, int MODE, bool BIG>
 __global__ void __launch_bounds__(BIG ? 480 : 288, BIG ? 1 : 2)
 k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_o,
                  const __grid_constant__ CUtensorMap tm_dy, TmaSweepParams P) {
   constexpr int NP = CB / 2;                                  // channel pairs per block
-  constexpr int NACC = (MODE == 0) ? (HAS_O ? 6 : 3) : (MODE == 2 ? (HAS_O ? 3 : 2) : (MODE == 3 ? 1 : 0));
+  constexpr int NACC = (MODE == 0 || MODE == 5) ? (HAS_O ? 6 : 3) : (MODE == 2 ? (HAS_O ? 3 : 2) : (MODE == 3 ? 1 : 0));
+  constexpr bool XFOLD = (MODE == 5);   // x = relu(z + o) is formed here: the o tile carries halo columns too
   constexpr bool HAS_DY = (MODE == 2 || MODE == 4);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
@@ -189,7 +191,7 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           unsigned char* sx = stages + (size_t)st * P.stage_bytes;
           mbar_arrive_expect_tx(&full[st], P.stage_bytes);
           tma_load_4d(sx, &tm_x, &full[st], cb * CB, -1, g * P.G, b);
-          if (HAS_O) tma_load_4d(sx + P.x_bytes, &tm_o, &full[st], cb * CB, 0, g * P.G, b);
+          if (HAS_O) tma_load_4d(sx + P.x_bytes, &tm_o, &full[st], cb * CB, XFOLD ? -1 : 0, g * P.G, b);
           if (HAS_DY) tma_load_4d(sx + P.x_bytes + (HAS_O ? P.o_bytes : 0), &tm_dy, &full[st], cb * CB, 0, g * P.G, b);
           if (++st == P.S) { st = 0; ph ^= 1; }
         }
@@ -208,7 +210,8 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   // thread reads its window at compile-time offsets from one per-thread base (no clamping, no o/dy masks).
   constexpr uint32_t CS = CB * ES;                      // bytes between adjacent columns
   const uint32_t xrow_bytes = (uint32_t)(P.NQ * kCols + 2) * CS;
-  const uint32_t orow_bytes = (uint32_t)(P.NQ * kCols) * CS;
+  const uint32_t orow_bytes = XFOLD ? xrow_bytes : (uint32_t)(P.NQ * kCols) * CS;
+  constexpr uint32_t OC = XFOLD ? CS : 0;   // byte offset of a thread's first own column inside its o row
   const uint32_t tbase = (uint32_t)(q * kCols) * CS + (uint32_t)p * 2 * ES;
   const bool ragged = (P.W % kCols) != 0;               // last column group is partial
   bool cvalid[kCols];
@@ -255,7 +258,8 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 #pragma unroll
     for (int i = 0; i < (NACC > 0 ? NACC : 1); ++i) { acc[i] = f2(0.f, 0.f); accb[i] = f2(0.f, 0.f); }
     // running pointer to this thread's first output column of the row being produced
-    T* yrow = (MODE == 1 || MODE == 3 || MODE == 4) ? static_cast<T*>(P.y) + (int64_t)b * P.bs_y + (int64_t)(q * kCols) * P.C + c : nullptr;
+    // MODE 5 writes x (row r, at fetch time); the others write the output row r-1
+    T* yrow = (MODE == 1 || MODE == 3 || MODE == 4 || MODE == 5) ? static_cast<T*>(P.y) + (int64_t)b * P.bs_y + (int64_t)(q * kCols) * P.C + c : nullptr;
     const int64_t y_row_stride = (int64_t)P.W * P.C;
     bool sv[kCols];
 #pragma unroll
@@ -280,6 +284,18 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             if (rr == 0) mbar_wait(&full[st_cur], ph_cur);
 #pragma unroll
             for (int j = 0; j < kWin; ++j) win[i][j] = lds_pair<T>(xa + j * CS);
+            if (XFOLD) {
+              // x = relu(z + identity) on the whole window (halo columns are 0 + 0), stored for the own columns
+#pragma unroll
+              for (int j = 0; j < kWin; ++j) {
+                const float2 t = fadd2(win[i][j], lds_pair<T>(oa + j * CS));
+                win[i][j] = f2(fmaxf(t.x, 0.f), fmaxf(t.y, 0.f));
+              }
+#pragma unroll
+              for (int j = 0; j < kCols; ++j)
+                if (sv[j]) stg_pair<T>(yrow + j * P.C, win[i][j + 1]);
+              yrow += y_row_stride;
+            }
             o_this = oa;
             xa += xrow_bytes;
             oa += orow_bytes;
@@ -306,11 +322,11 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             for (int j = 0; j < kCols; ++j) {
               float2 v = act2<ACT>(u4[j]);
               float2 ov = f2(0.f, 0.f), gv = f2(0.f, 0.f);
-              if (HAS_O) ov = lds_pair<T>(ob + j * CS);
+              if (HAS_O) ov = lds_pair<T>(ob + OC + j * CS);
               if (HAS_DY) gv = lds_pair<T>(ob + (HAS_O ? P.o_bytes : 0) + j * CS);
               const float2 xc = mid[j + 1];
               float2(&A)[NACC > 0 ? NACC : 1] = (j & 1) ? accb : acc;
-              if (MODE == 0) {
+              if (MODE == 0 || MODE == 5) {
                 if (ragged && !cvalid[j]) v = f2(0.f, 0.f);
                 A[0] = fadd2(A[0], xc);
                 A[1] = fadd2(A[1], v);
