@@ -205,6 +205,39 @@ int mrla_nchw_to_nhwc(const void* src, void* dst, int B, int C, int HW, int dtyp
 /* x = relu(z + idt) over n contiguous elements (16-byte aligned, n multiple of the 16-byte vector width). */
 int mrla_add_relu(const void* z, const void* idt, void* x, int64_t n, int dtype, void* stream);
 
+/* Channels-last BatchNorm2d (+ optional ReLU): the bottleneck's bn1/bn2/bn3 and the stem BN on either side of the MRLA
+ * tail.  Replaces at::batch_norm (+ at::relu) and their backward for NHWC activations
+ * viewed as x[M = B*H*W, C]; PyTorch runs bf16 channels_last BN on its native (non-cuDNN) kernels. */
+typedef struct MrlaBnArgs {
+  int64_t M;               /* rows = B*H*W                                                        */
+  int32_t C;               /* channels, multiple of 8, <= 2048                                    */
+  int32_t dtype;           /* MRLA_F32 / MRLA_BF16 / MRLA_F16                                     */
+  int32_t relu;            /* 1: y = relu(bn(x))                                                  */
+  int32_t training;        /* 1: batch statistics; 0: running statistics                          */
+  int32_t update_running;  /* 1: update running_mean / running_var in place (training only)       */
+  int32_t reserved0;
+  float eps, momentum;
+  const void* x;           /* [M,C]                                                               */
+  void* y;                 /* [M,C] (forward)                                                     */
+  const float* gamma;      /* [C] or NULL                                                         */
+  const float* beta;       /* [C] or NULL                                                         */
+  float* running_mean;     /* [C]                                                                 */
+  float* running_var;      /* [C]                                                                 */
+  float* stats;            /* [2,C] mean, rstd actually used   (saved for backward)               */
+  float* coef;             /* [2,C] a = gamma*rstd, b = beta - a*mean (saved for backward)        */
+  const void* dy;          /* [M,C] (backward)                                                    */
+  void* dx;                /* [M,C]                                                               */
+  float* dgamma;           /* [C] or NULL                                                         */
+  float* dbeta;            /* [C] or NULL                                                         */
+  float* scratch;          /* mrla_bn_scratch_bytes()                                             */
+  size_t scratch_bytes;
+} MrlaBnArgs;
+
+size_t mrla_sizeof_bn_args(void);
+size_t mrla_bn_scratch_bytes(const MrlaBnArgs* a);
+int mrla_bn_forward(const MrlaBnArgs* a, void* stream);
+int mrla_bn_backward(const MrlaBnArgs* a, void* stream);
+
 /* Number of kernel launches the last forward / backward call on this thread enqueued
  * (bench.py reports it as gpu_launches). */
 int mrla_last_launch_count(void);

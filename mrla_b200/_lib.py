@@ -57,6 +57,18 @@ class MrlaBaseArgs(ctypes.Structure):
     )
 
 
+class MrlaBnArgs(ctypes.Structure):
+    """Mirror of `struct MrlaBnArgs` (include/mrla_b200.h)."""
+    _fields_ = (
+        [("M", _i64)]
+        + [(n, _i32) for n in ("C", "dtype", "relu", "training", "update_running", "reserved0")]
+        + [("eps", _f32), ("momentum", _f32)]
+        + [(n, _vp) for n in ("x", "y", "gamma", "beta", "running_mean", "running_var", "stats", "coef", "dy", "dx",
+                              "dgamma", "dbeta", "scratch")]
+        + [("scratch_bytes", ctypes.c_size_t)]
+    )
+
+
 _lib = None
 _lock = threading.Lock()
 
@@ -100,6 +112,15 @@ def lib() -> ctypes.CDLL:
         L.mrla_sizeof_base_args.restype = ctypes.c_size_t
         if L.mrla_sizeof_base_args() != ctypes.sizeof(MrlaBaseArgs):
             raise RuntimeError("MrlaBaseArgs layout mismatch between _lib.py and include/mrla_b200.h")
+        L.mrla_sizeof_bn_args.restype = ctypes.c_size_t
+        if L.mrla_sizeof_bn_args() != ctypes.sizeof(MrlaBnArgs):
+            raise RuntimeError("MrlaBnArgs layout mismatch between _lib.py and include/mrla_b200.h")
+        L.mrla_bn_scratch_bytes.restype = ctypes.c_size_t
+        L.mrla_bn_scratch_bytes.argtypes = [ctypes.POINTER(MrlaBnArgs)]
+        for d in ("forward", "backward"):
+            f = getattr(L, f"mrla_bn_{d}")
+            f.restype = ctypes.c_int
+            f.argtypes = [ctypes.POINTER(MrlaBnArgs), ctypes.c_void_p]
         for name, st in (("light", MrlaLightArgs), ("base", MrlaBaseArgs)):
             f = getattr(L, f"mrla_{name}_bwd_scratch_bytes")
             f.restype = ctypes.c_size_t

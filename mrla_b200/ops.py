@@ -562,3 +562,106 @@ def base_tail(x, prev_k, prev_v, wq, wk, wv, gamma=None, beta=None, running_mean
     K._mrla_cache = cache
     K._mrla_token = token if token.requires_grad else None
     return y, K, V
+
+
+# ===================================================================================== BatchNorm (+ReLU) producer
+def bn_act_eligible(x: torch.Tensor) -> bool:
+    """Channels-last dense [B,C,H,W] (or [M,C]) CUDA activation the NHWC BatchNorm kernels can take."""
+    if not x.is_cuda or x.dtype not in _DTYPES:
+        return False
+    if x.dim() == 2:
+        return x.is_contiguous() and x.shape[1] % 8 == 0 and 8 <= x.shape[1] <= 2048 and x.data_ptr() % 16 == 0
+    if x.dim() != 4:
+        return False
+    B, C, H, W = x.shape
+    lay = _layout_of(x)
+    return (lay is not None and lay[0] == _lib.NHWC and lay[1] == C * H * W and C % 8 == 0 and 8 <= C <= 2048
+            and H * W > 1 and x.data_ptr() % 16 == 0)
+
+
+class _BnAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, training, update_running, momentum, eps, relu):
+        L = _lib.lib()
+        if x.dim() == 4:
+            B, C, H, W = x.shape
+            M = B * H * W
+            y = _empty_like_layout(x, _lib.NHWC)
+        else:
+            M, C = x.shape
+            y = torch.empty_like(x)
+        f32 = dict(dtype=torch.float32, device=x.device)
+        stats = torch.empty((2, C), **f32)
+        coef = torch.empty((2, C), **f32)
+        w32, b32 = _f32(weight), _f32(bias)
+        a = _lib.MrlaBnArgs()
+        a.M, a.C, a.dtype = M, C, _DTYPES[x.dtype]
+        a.relu, a.training, a.update_running = int(relu), int(training), int(update_running)
+        a.eps, a.momentum = eps, momentum
+        a.x, a.y, a.gamma, a.beta = _ptr(x), _ptr(y), _ptr(w32), _ptr(b32)
+        a.running_mean, a.running_var = _ptr(running_mean), _ptr(running_var)
+        a.stats, a.coef = _ptr(stats), _ptr(coef)
+        nbytes = L.mrla_bn_scratch_bytes(ctypes.byref(a))
+        scratch = torch.empty((max(nbytes, 4) + 3) // 4, **f32)
+        a.scratch, a.scratch_bytes = _ptr(scratch), scratch.numel() * 4
+        _lib.check(L.mrla_bn_forward(ctypes.byref(a), _stream()), "mrla_bn_forward")
+        launch_counter["fwd"] += L.mrla_last_launch_count()
+        ctx.meta = (M, C, bool(relu), bool(training), eps, momentum)
+        ctx.param_meta = [(p.shape, p.dtype, p.stride()) if p is not None else None for p in (weight, bias)]
+        ctx.save_for_backward(x, w32, stats, coef)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _lib.lib()
+        x, w32, stats, coef = ctx.saved_tensors
+        M, C, relu, training, eps, momentum = ctx.meta
+        if dy.dtype != x.dtype:
+            dy = dy.to(x.dtype)
+        if x.dim() == 4:
+            lay = _layout_of(dy)
+            if lay is None or lay[0] != _lib.NHWC or lay[1] != x[0].numel():
+                dy = dy.contiguous(memory_format=torch.channels_last)
+                if _layout_of(dy) is None or _layout_of(dy)[0] != _lib.NHWC:
+                    dy = dy.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+            dx = _empty_like_layout(x, _lib.NHWC)
+        else:
+            dy = dy.contiguous()
+            dx = torch.empty_like(x)
+        f32 = dict(dtype=torch.float32, device=x.device)
+        dgb = torch.empty((2, C), **f32)
+        a = _lib.MrlaBnArgs()
+        a.M, a.C, a.dtype = M, C, _DTYPES[x.dtype]
+        a.relu, a.training = int(relu), int(training)
+        a.eps, a.momentum = eps, momentum
+        a.x, a.gamma, a.stats, a.coef = _ptr(x), _ptr(w32), _ptr(stats), _ptr(coef)
+        a.dy, a.dx, a.dgamma, a.dbeta = _ptr(dy), _ptr(dx), _ptr(dgb[0]), _ptr(dgb[1])
+        nbytes = L.mrla_bn_scratch_bytes(ctypes.byref(a))
+        scratch = torch.empty((max(nbytes, 4) + 3) // 4, **f32)
+        a.scratch, a.scratch_bytes = _ptr(scratch), scratch.numel() * 4
+        _lib.check(L.mrla_bn_backward(ctypes.byref(a), _stream()), "mrla_bn_backward")
+        launch_counter["bwd"] += L.mrla_last_launch_count()
+        dw = _like_param(dgb[0], ctx.param_meta[0]) if ctx.param_meta[0] is not None else None
+        db = _like_param(dgb[1], ctx.param_meta[1]) if ctx.param_meta[1] is not None else None
+        return dx, dw, db, None, None, None, None, None, None, None
+
+
+def bn_act(x, bn: "torch.nn.BatchNorm2d", relu: bool = False) -> torch.Tensor:
+    """BatchNorm2d (+ReLU) of the bottleneck on the fused NHWC kernels, with nn.BatchNorm2d semantics (train / eval,
+    running statistics, momentum=None cumulative average, affine or not).  Activations that are not channels-last
+    (or have C % 8 != 0) go through the library's own batch_norm (+relu) — they are not on the MRLA path."""
+    use_batch = bn.training or bn.running_mean is None
+    if not bn_act_eligible(x) or (not use_batch and bn.running_mean is None):
+        y = bn(x)
+        return torch.relu(y) if relu else y
+    update = bn.training and bn.track_running_stats and bn.running_mean is not None
+    if update:
+        bn.num_batches_tracked += 1
+        momentum = bn.momentum if bn.momentum is not None else 1.0 / float(int(bn.num_batches_tracked))
+    else:
+        momentum = 0.0
+    rm, rv = bn.running_mean, bn.running_var
+    if rm is not None and rm.dtype != torch.float32:
+        y = bn(x)   # exotic buffer dtype: leave to the library
+        return torch.relu(y) if relu else y
+    return _BnAct.apply(x, bn.weight, bn.bias, rm, rv, use_batch, update, momentum, bn.eps, relu)

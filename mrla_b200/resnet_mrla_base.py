@@ -11,6 +11,7 @@ import torch.nn.functional as F
 from . import _lib
 from .drop import DropPath
 from .modules.mrla_base_module import mrla_base_layer
+from .ops import bn_act
 from .resnet_mrla_light import _bn_effective_momentum, _conv1x1, _conv3x3
 
 __all__ = ["ResNet_mrlab", "MRLA_Bottleneck", "mrla_module", "mrla_base_block_tail", "resnet50_mrlab",
@@ -77,10 +78,16 @@ class MRLA_Bottleneck(nn.Module):
         self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
 
     def forward(self, x, prev_k, prev_v):
-        identity = x if self.downsample is None else self.downsample(x)
-        out = self.relu(self.bn1(self.conv1(x)))
-        out = self.relu(self.bn2(self.conv2(out)))
-        out = self.relu(self.bn3(self.conv3(out)) + identity)
+        if self.downsample is None:
+            identity = x
+        elif isinstance(self.downsample, nn.Sequential) and len(self.downsample) == 2 \
+                and isinstance(self.downsample[1], nn.BatchNorm2d):
+            identity = bn_act(self.downsample[0](x), self.downsample[1])
+        else:
+            identity = self.downsample(x)
+        out = bn_act(self.conv1(x), self.bn1, relu=True)
+        out = bn_act(self.conv2(out), self.bn2, relu=True)
+        out = self.relu(bn_act(self.conv3(out), self.bn3) + identity)
         return mrla_base_block_tail(out, prev_k, prev_v, self.mrla, self.bn_mrla, self.drop_path, relu=True)
 
 
@@ -141,7 +148,7 @@ class ResNet_mrlab(nn.Module):
         return nn.ModuleList(seq)
 
     def forward_features(self, x):
-        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.maxpool(bn_act(self.conv1(x), self.bn1, relu=True))
         k = v = None
         for stage in self.stages:
             for blk in stage:

@@ -16,7 +16,7 @@ import torch.nn.functional as F
 from . import _lib
 from .drop import DropPath
 from .modules.mrla_light_module import mrla_light_layer
-from .ops import light_tail
+from .ops import bn_act, light_tail
 
 __all__ = ["ResNet_mrlal", "MRLA_Bottleneck", "mrla_module", "mrla_light_block_tail",
            "resnet50_mrlal", "resnet101_mrlal"]
@@ -103,10 +103,17 @@ class MRLA_Bottleneck(nn.Module):
         self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
 
     def forward(self, x):
-        identity = x if self.downsample is None else self.downsample(x)
-        out = self.relu(self.bn1(self.conv1(x)))
-        out = self.relu(self.bn2(self.conv2(out)))
-        out = self.bn3(self.conv3(out))
+        # conv -> cuDNN; BatchNorm(+ReLU) -> fused NHWC kernels (ops.bn_act; library batch_norm for other layouts)
+        if self.downsample is None:
+            identity = x
+        elif isinstance(self.downsample, nn.Sequential) and len(self.downsample) == 2 \
+                and isinstance(self.downsample[1], nn.BatchNorm2d):
+            identity = bn_act(self.downsample[0](x), self.downsample[1])
+        else:
+            identity = self.downsample(x)
+        out = bn_act(self.conv1(x), self.bn1, relu=True)
+        out = bn_act(self.conv2(out), self.bn2, relu=True)
+        out = bn_act(self.conv3(out), self.bn3)
         # `out += identity; relu` (reference :113-114) is folded into the tail op
         return mrla_light_block_tail(out, identity, self.mrla, self.bn_mrla, self.drop_path, pre_add_relu=True)
 
@@ -165,7 +172,7 @@ class ResNet_mrlal(nn.Module):
         return nn.Sequential(*seq)
 
     def forward_features(self, x):
-        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.maxpool(bn_act(self.conv1(x), self.bn1, relu=True))
         return self.layer4(self.layer3(self.layer2(self.layer1(x))))
 
     def forward(self, x):
