@@ -76,17 +76,18 @@ __global__ void __launch_bounds__(256) k_bn_stats(const T* __restrict__ x, float
 }
 
 // part [nparts, 2, C] -> mean, rstd (saved) ; coef [2,C]: a = γ r, b = β − γ r μ ; running stats
-static __global__ void __launch_bounds__(256) k_bn_finalize(const float* __restrict__ part, int nparts, int C, double n,
+static __global__ void __launch_bounds__(1024) k_bn_finalize(const float* __restrict__ part, int nparts, int C, double n,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float* __restrict__ running_mean, float* __restrict__ running_var,
                                                             float* __restrict__ stats, float* __restrict__ coef, float eps,
                                                             float momentum, int training, int update_running) {
-  __shared__ double r1[8][33], r2[8][33];
+  __shared__ double r1[32][33], r2[32][33];
   const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   double s1 = 0.0, s2 = 0.0;
   if (c < C && training)
-    for (int p = pl; p < nparts; p += 8) {
+#pragma unroll 4
+    for (int p = pl; p < nparts; p += 32) {
       s1 += (double)part[((size_t)p * 2) * C + c];
       s2 += (double)part[((size_t)p * 2 + 1) * C + c];
     }
@@ -97,7 +98,7 @@ static __global__ void __launch_bounds__(256) k_bn_finalize(const float* __restr
   double mu, r;
   if (training) {
     double a1 = 0.0, a2 = 0.0;
-    for (int j = 0; j < 8; ++j) { a1 += r1[j][cl]; a2 += r2[j][cl]; }
+    for (int j = 0; j < 32; ++j) { a1 += r1[j][cl]; a2 += r2[j][cl]; }
     mu = a1 / n;
     double var = a2 / n - mu * mu;
     if (var < 0.0) var = 0.0;
@@ -177,17 +178,18 @@ __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const T* __restrict__ dy,
 
 // part [nparts,2,C] (Σdz, Σdz·x) -> dγ dβ ; bcoef [3,C]: dx = A dz + B x + Cc
 //   train: dx = γ r (dz − m1 − x̂ m2), x̂ = r (x − μ), m1 = Σdz/n, m2 = Σdz x̂ / n ;  eval: dx = γ r dz
-static __global__ void __launch_bounds__(256) k_bn_bwd_finalize(const float* __restrict__ part, int nparts, int C,
+static __global__ void __launch_bounds__(1024) k_bn_bwd_finalize(const float* __restrict__ part, int nparts, int C,
                                                                 double n, const float* __restrict__ gamma,
                                                                 const float* __restrict__ stats,
                                                                 float* __restrict__ bcoef, float* __restrict__ dgamma,
                                                                 float* __restrict__ dbeta, int training) {
-  __shared__ double r1[8][33], r2[8][33];
+  __shared__ double r1[32][33], r2[32][33];
   const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   double s1 = 0.0, s2 = 0.0;
   if (c < C)
-    for (int p = pl; p < nparts; p += 8) {
+#pragma unroll 4
+    for (int p = pl; p < nparts; p += 32) {
       s1 += (double)part[((size_t)p * 2) * C + c];
       s2 += (double)part[((size_t)p * 2 + 1) * C + c];
     }
@@ -196,7 +198,7 @@ static __global__ void __launch_bounds__(256) k_bn_bwd_finalize(const float* __r
   __syncthreads();
   if (pl != 0 || c >= C) return;
   double a1 = 0.0, a2 = 0.0;
-  for (int j = 0; j < 8; ++j) { a1 += r1[j][cl]; a2 += r2[j][cl]; }
+  for (int j = 0; j < 32; ++j) { a1 += r1[j][cl]; a2 += r2[j][cl]; }
   const double mu = stats[c], r = stats[C + c], ga = gamma ? (double)gamma[c] : 1.0;
   const double dbe = a1, dga = r * (a2 - mu * a1);   // Σdz x̂
   if (dbeta) dbeta[c] = (float)dbe;

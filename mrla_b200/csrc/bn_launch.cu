@@ -16,7 +16,7 @@ static int bn_plan(const MrlaBnArgs* a, BnShape* s) {
   if (s->RL < 1) return MRLA_ERR_SHAPE;
   const int64_t rows_per_pass = s->RL;
   int64_t grid = (a->M + rows_per_pass * 8 - 1) / (rows_per_pass * 8);   // >= 8 rows per thread
-  if (grid > kNumSMs * 4) grid = kNumSMs * 4;
+  if (grid > kNumSMs * 3) grid = kNumSMs * 3;
   if (grid < 1) grid = 1;
   s->nparts = (int)grid;
   return MRLA_OK;
@@ -30,7 +30,7 @@ static int bn_forward_t(const MrlaBnArgs& a, const BnShape& s, cudaStream_t st) 
     k_bn_stats<T><<<s.nparts, 256, 256 * 2 * kSV * sizeof(float), st>>>(x, a.scratch, s);
     MRLA_CHECK_LAUNCH();
   }
-  k_bn_finalize<<<(a.C + 31) / 32, 256, 0, st>>>(a.scratch, s.nparts, a.C, (double)a.M, a.gamma, a.beta, a.running_mean,
+  k_bn_finalize<<<(a.C + 31) / 32, 1024, 0, st>>>(a.scratch, s.nparts, a.C, (double)a.M, a.gamma, a.beta, a.running_mean,
                                                  a.running_var, a.stats, a.coef, a.eps, a.momentum, a.training,
                                                  a.update_running);
   MRLA_CHECK_LAUNCH();
@@ -50,7 +50,7 @@ static int bn_backward_t(const MrlaBnArgs& a, const BnShape& s, cudaStream_t st)
   if (a.relu) k_bn_bwd_reduce<T, true><<<s.nparts, 256, sm, st>>>(dy, x, a.coef, a.scratch, s);
   else k_bn_bwd_reduce<T, false><<<s.nparts, 256, sm, st>>>(dy, x, a.coef, a.scratch, s);
   MRLA_CHECK_LAUNCH();
-  k_bn_bwd_finalize<<<(a.C + 31) / 32, 256, 0, st>>>(a.scratch, s.nparts, a.C, (double)a.M, a.gamma, a.stats, bcoef,
+  k_bn_bwd_finalize<<<(a.C + 31) / 32, 1024, 0, st>>>(a.scratch, s.nparts, a.C, (double)a.M, a.gamma, a.stats, bcoef,
                                                      a.dgamma, a.dbeta, a.training);
   MRLA_CHECK_LAUNCH();
   if (a.relu) k_bn_bwd_apply<T, true><<<s.nparts, 256, 0, st>>>(dy, x, dx, a.coef, bcoef, s);
