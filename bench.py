@@ -209,7 +209,7 @@ def run_product_arm(args):
     model = resnet50_mrlal(drop_path=args.drop_path).to(dev).to(memory_format=torch.channels_last).train()
     opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)  # reference train.py:199
     net = model
-    if world > 1:
+    if world > 1 and args.no_graph:   # eager path: the reference's DDP wrap; the graph path all-reduces a flat buffer
         net = nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)
     crit = nn.CrossEntropyLoss().to(dev)
     gen = torch.Generator(device="cpu").manual_seed(1 + rank)
@@ -245,43 +245,72 @@ def run_product_arm(args):
         step(dev_img, dev_lbl)
     barrier()
 
-    # ---- whole-step CUDA graph (fwd + loss + bwd + SGD on static buffers): the step is ~800 kernel launches and
-    # the Python/launch path alone costs ~34 ms per step on this host, which would cap a 37 ms GPU step.
-    graph = None
+    # ---- CUDA graphs (static buffers): graph A = forward + loss + backward into ONE flat fp32 gradient buffer,
+    # [N > 1: one NCCL all-reduce (AVG) of that buffer over NVLink/NVSwitch], graph B = SGD update.
+    # The step is ~800 kernel launches and the Python/launch path alone costs ~34 ms per step on this host, which
+    # would cap a ~36 ms GPU step; the reference's DDP (train.py:174) is replaced by the explicit all-reduce of the
+    # same gradients (103 MB fp32, ~0.3 ms at NVLink bandwidth, so overlap with backward is not needed).
+    graph_a = graph_b = None
     static_loss = None
     launches_per_step = None
+    flat = None
     if not args.no_graph:
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(3):
-                    step(dev_img, dev_lbl)
-            torch.cuda.current_stream().wait_stream(side)
+        params = [p_ for p_ in model.parameters() if p_.requires_grad]
+        flat = torch.zeros(sum(p_.numel() for p_ in params), dtype=torch.float32, device=dev)
+
+        def grad_view(p_, seg):
+            if p_.dim() == 4 and not p_.is_contiguous() and p_.is_contiguous(memory_format=torch.channels_last):
+                k_, c_, r_, s_ = p_.shape
+                return seg.view(k_, r_, s_, c_).permute(0, 3, 1, 2)   # same strides as the channels_last weight
+            return seg.view(p_.shape)
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            if world > 1:
+                for p_ in model.parameters():
+                    dist.broadcast(p_.data, 0)
+                for b_ in model.buffers():
+                    dist.broadcast(b_.data, 0)
             opt.zero_grad(set_to_none=True)
-            l0 = ops.launch_counter["fwd"] + ops.launch_counter["bwd"]
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            off = 0
+            for p_ in params:
+                p_.grad = grad_view(p_, flat[off:off + p_.numel()])
+                off += p_.numel()
+            for _ in range(3):   # warm-up of the exact captured sequence on the capture stream
+                flat.zero_()
                 with torch.autocast("cuda", dtype=torch.bfloat16):
-                    out = net(dev_img)
-                static_loss = crit(out.float(), dev_lbl)
-                static_loss.backward()
+                    out = model(dev_img)
+                crit(out.float(), dev_lbl).backward()
+                if world > 1:
+                    dist.all_reduce(flat, op=dist.ReduceOp.AVG)
                 opt.step()
-            launches_per_step = ops.launch_counter["fwd"] + ops.launch_counter["bwd"] - l0
-            graph.replay()
-            torch.cuda.synchronize()
-        except Exception as exc:  # capture not possible (e.g. DDP/NCCL constraints): fall back to eager launches
-            if rank == 0:
-                print(f"bench.py: CUDA-graph capture failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
-            graph = None
-            torch.cuda.synchronize()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        l0 = ops.launch_counter["fwd"] + ops.launch_counter["bwd"]
+        graph_a, graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph_a):
+            flat.zero_()
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = model(dev_img)
+            static_loss = crit(out.float(), dev_lbl)
+            static_loss.backward()
+        with torch.cuda.graph(graph_b, pool=graph_a.pool()):
+            opt.step()
+        launches_per_step = ops.launch_counter["fwd"] + ops.launch_counter["bwd"] - l0
+        torch.cuda.synchronize()
     barrier()
 
     def run_step():
-        if graph is not None:
-            graph.replay()
+        if graph_a is not None:
+            graph_a.replay()
+            if world > 1:
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            graph_b.replay()
             return static_loss
         return step(dev_img, dev_lbl)
+
+    graph = graph_a
 
     # ---- timed region 1: inputs resident in HBM ----
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -400,9 +429,11 @@ def run_product_arm(args):
         "config": {"workload": "resnet50_mrlal training step (fwd+loss+bwd+SGD), BASELINE configs[1]",
                    "model": "resnet50_mrlal", "per_gpu_batch": B, "global_batch": B * world, "image": "3x224x224",
                    "precision": "bf16 autocast, fp32 master weights", "memory_format": "channels_last",
-                   "drop_path": args.drop_path, "parallelism": f"dp{world}" + (" (DDP/NCCL)" if world > 1 else ""),
+                   "drop_path": args.drop_path,
+                   "parallelism": f"dp{world}" + ((" (flat-gradient NCCL all-reduce)" if graph is not None else " (DDP/NCCL)")
+                                                  if world > 1 else ""),
                    "l2": "inputs exceed L2 (per-step activations >> 126 MB); no explicit flush",
-                   "launch": "whole step replayed as one CUDA graph" if graph is not None else "eager launches"},
+                   "launch": "CUDA graphs (fwd+bwd | all-reduce | SGD)" if graph is not None else "eager launches"},
         "clocks": clocks,
         "e2e": {"value": round(world * B * K / (ms_e2e / 1e3), 2), "unit": "img/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / K, 3), "last_loss": round(last_loss, 4)},
