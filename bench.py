@@ -317,10 +317,13 @@ def run_product_arm(args):
     l0 = ops.launch_counter["fwd"] + ops.launch_counter["bwd"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    torch.cuda.profiler.start()   # `ncu --profile-from-start off` then captures exactly the timed steps (all threads)
     e0.record()
     for _ in range(K):
         run_step()
     e1.record()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = (launches_per_step * K) if graph is not None else (ops.launch_counter["fwd"] + ops.launch_counter["bwd"] - l0)
