@@ -4,6 +4,7 @@
 #include "light_mid.cuh"
 #include "light_sweeps.cuh"
 #include "light_nhwc_tma.cuh"
+#include "light_nhwc_ring.cuh"
 #include "layout_kernels.cuh"
 
 namespace mrla {
@@ -136,6 +137,7 @@ int launch_tma_sweep(const MrlaLightArgs& a, cudaStream_t st, const TmaPlan& p, 
   TmaSweepParams P;
   P.B = a.B; P.C = a.C; P.H = a.H; P.W = a.W;
   P.G = p.G; P.S = p.S; P.NQ = p.NQ; P.ncb = p.ncb; P.items = p.items; P.cons_threads = p.cons_threads;
+  P.rev = (MODE == 1) ? 1 : 0;   // sweep 2 meets the end of the batch sweep 1 just left in L2
   P.x_bytes = p.x_bytes; P.o_bytes = p.o_bytes; P.stage_bytes = p.stage_bytes;
   P.wv = a.wv; P.mom = mom; P.coef = a.coef; P.y = a.y; P.bs_y = a.bs_y; P.res = a.residual ? 1.f : 0.f;
   P.wv_part = (MODE == 4) ? mom : nullptr;   // MODE 4 passes the partial buffer through `mom`
@@ -250,79 +252,93 @@ int launch_tma_bwd(const MrlaLightArgs& a, cudaStream_t st, const TmaBwdPlan& p,
   return MRLA_OK;
 }
 
-// v3 sweep B (T ring): full-width rows, same tiles as sweep A
-inline bool make_tma_ring_plan(const MrlaLightArgs& a, TmaBwdPlan* p) {
-  if (a.layout != MRLA_NHWC || a.C % 8 || a.W > 56) return false;
+// v4 sweep B (T ring, light_nhwc_ring.cuh): full-width rows, one image row per stage, one channel block per CTA.
+// TmaBwdPlan::big doubles as the column count per thread: big (KC = 8, one CTA per SM) or small (KC = 4, two per SM).
+inline bool ring_plan_try(const MrlaLightArgs& a, int KC, int CB, TmaBwdPlan* p) {
   const int es = a.dtype == MRLA_F32 ? 4 : 2;
-  const int NQ = (a.W + kCols - 1) / kCols;
-  // big: one CTA of up to 448 consumers per SM; small: up to 128 consumers, three CTAs per SM
-  int CB = 0;
-  for (int cb : {256, 128, 64})
-    if (NQ * cb / 2 <= 448 && NQ * cb / 2 > 256 && a.C % cb == 0) { CB = cb; break; }
-  if (CB == 0)
-    for (int cb : {256, 128, 64})
-      if (NQ * cb / 2 <= 128 && (a.C % cb == 0 || cb == 64)) { CB = cb; break; }
-  if (CB == 0) return false;
-  if (a.act == MRLA_ACT_GELU && CB == 256) return false;
+  const int NQ = (a.W + KC - 1) / KC;
   p->cons_threads = NQ * (CB / 2);
-  p->big = p->cons_threads > 256;
-  const size_t ring = (size_t)4 * (NQ * kCols + 2) * (CB / 2) * sizeof(float2);
-  const size_t budget = (size_t)(p->big ? 200 : 66) * 1024;
+  p->big = (KC == 8);
+  const uint32_t xrow = (uint32_t)(NQ * KC + 2) * CB * es, trow = (uint32_t)(NQ * KC) * CB * es;
+  // 4 T-ring slots of 128-bit column pairs + 3 staging buffers of one dX row and one dO row for the TMA stores
+  const size_t ring = (size_t)4 * (KC / 2 * NQ + 2) * (CB / 2) * 16 + (size_t)3 * 2 * trow;
+  const size_t budget = (size_t)(p->big ? 226 : 100) * 1024;   // sm_100a: 227 KB dynamic shared memory per CTA
   if (ring + 8192 > budget) return false;
-  const uint32_t xrow = (uint32_t)(NQ * kCols + 2) * CB * es, trow = (uint32_t)(NQ * kCols) * CB * es;
-  const uint32_t rowtot = xrow + 2 * trow;
-  int G = (int)(((budget - ring) / 5) / rowtot);
-  if (G < 1) G = 1;
-  if (G > a.H) G = a.H;
-  p->CB = CB; p->NQ = NQ; p->NT = 1; p->WT = a.W; p->G = G;
-  p->x_bytes = (uint32_t)G * xrow;
-  p->t_bytes = (uint32_t)G * trow;
-  p->stage_bytes = p->x_bytes + 2 * p->t_bytes;
+  p->CB = CB; p->NQ = NQ; p->NT = 1; p->WT = a.W; p->G = 1;
+  p->x_bytes = xrow;
+  p->t_bytes = trow;
+  p->stage_bytes = xrow + 2 * trow;
   int S = (int)((budget - ring) / p->stage_bytes);
   if (S > 8) S = 8;
-  if (S < 2) return false;
+  if (S < 3) return false;
   p->S = S;
   p->ncb = (a.C + CB - 1) / CB;
   p->items = p->ncb * a.B;
-  const int slots = p->big ? kNumSMs : 3 * kNumSMs;
-  int grid = p->items < slots ? p->items : slots;
-  p->ipc = (p->items + grid - 1) / grid;
-  p->grid = (p->items + p->ipc - 1) / p->ipc;
-  p->maxslots = (a.B + p->ipc - 1) / p->ipc + 1;
+  const int slots = p->big ? kNumSMs : 2 * kNumSMs;
+  int cpc = slots / p->ncb;
+  if (cpc < 1) cpc = 1;
+  if (cpc > a.B) cpc = a.B;
+  p->ipc = (a.B + cpc - 1) / cpc;
+  p->grid = p->ncb * cpc;
+  p->maxslots = cpc;
   p->smem = 256 + (size_t)S * p->stage_bytes + ring;
   return true;
 }
 
+inline bool make_tma_ring_plan(const MrlaLightArgs& a, TmaBwdPlan* p) {
+  if (a.layout != MRLA_NHWC || a.C % 8 || a.W > 64 || a.H < 3) return false;
+  // big: 8 columns per thread, 129..256 threads, one CTA per SM; small: 4 columns per thread, up to 128 threads, two
+  // CTAs per SM.  First candidate whose ring + staging + >= 4 pipeline stages fit in shared memory.
+  for (int cb : {256, 128, 64}) {
+    const int n = ((a.W + 7) / 8) * cb / 2;
+    if (a.act == MRLA_ACT_GELU && cb == 256) continue;
+    if (n <= 256 && n > 128 && (a.C % cb == 0 || (cb == 64 && a.C > 64)) && ring_plan_try(a, 8, cb, p)) return true;
+  }
+  for (int cb : {256, 128, 64}) {
+    const int n = ((a.W + 3) / 4) * cb / 2;
+    if (a.act == MRLA_ACT_GELU && cb == 256) continue;
+    if (n <= 128 && (a.C % cb == 0 || cb == 64) && ring_plan_try(a, 4, cb, p)) return true;
+  }
+  return false;
+}
+
 template <typename T, int ACT>
 int launch_tma_bwd_ring(const MrlaLightArgs& a, cudaStream_t st, const TmaBwdPlan& p, float* wv_part) {
-  CUtensorMap tx, tdy, to;
-  if (make_nhwc_tmap(&tx, a.x, a.dtype, a.B, a.C, a.H, a.W, a.bs_x, p.CB, p.NQ * kCols + 2, p.G)) return MRLA_ERR_UNSUPPORTED;
-  if (make_nhwc_tmap(&tdy, a.dy, a.dtype, a.B, a.C, a.H, a.W, a.bs_dy, p.CB, p.NQ * kCols, p.G)) return MRLA_ERR_UNSUPPORTED;
-  if (make_nhwc_tmap(&to, a.o, a.dtype, a.B, a.C, a.H, a.W, a.bs_o, p.CB, p.NQ * kCols, p.G)) return MRLA_ERR_UNSUPPORTED;
-  cudaError_t e = cudaMemsetAsync(wv_part, 0, (size_t)p.maxslots * a.C * 9 * sizeof(float), st);
-  if (e != cudaSuccess) return (int)e;
+  const int KC = p.big ? 8 : 4;
+  CUtensorMap tx, tdy, to, tdx, tdo;
+  if (make_nhwc_tmap(&tx, a.x, a.dtype, a.B, a.C, a.H, a.W, a.bs_x, p.CB, p.NQ * KC + 2, 1)) return MRLA_ERR_UNSUPPORTED;
+  if (make_nhwc_tmap(&tdy, a.dy, a.dtype, a.B, a.C, a.H, a.W, a.bs_dy, p.CB, p.NQ * KC, 1)) return MRLA_ERR_UNSUPPORTED;
+  if (make_nhwc_tmap(&to, a.o, a.dtype, a.B, a.C, a.H, a.W, a.bs_o, p.CB, p.NQ * KC, 1)) return MRLA_ERR_UNSUPPORTED;
+  if (make_nhwc_tmap(&tdx, a.dx, a.dtype, a.B, a.C, a.H, a.W, a.bs_dx, p.CB, p.NQ * KC, 1)) return MRLA_ERR_UNSUPPORTED;
+  if (make_nhwc_tmap(&tdo, a.dout, a.dtype, a.B, a.C, a.H, a.W, a.bs_do, p.CB, p.NQ * KC, 1)) return MRLA_ERR_UNSUPPORTED;
+  cudaError_t e = cudaSuccess;
   TmaBwdParams P;
   P.B = a.B; P.C = a.C; P.H = a.H; P.W = a.W;
-  P.G = p.G; P.S = p.S; P.NQ = p.NQ; P.ncb = p.ncb; P.NT = 1; P.WT = a.W; P.items = p.items; P.ipc = p.ipc;
-  P.cons_threads = p.cons_threads; P.maxslots = p.maxslots;
+  P.G = 1; P.S = p.S; P.NQ = p.NQ; P.ncb = p.ncb; P.NT = 1; P.WT = a.W; P.items = p.items; P.ipc = p.ipc;
+  P.cons_threads = p.cons_threads; P.maxslots = p.maxslots; P.cpc = p.maxslots;
   P.x_bytes = p.x_bytes; P.t_bytes = p.t_bytes; P.stage_bytes = p.stage_bytes;
   P.wv = a.wv; P.lam = a.lam; P.bcoef = a.bcoef; P.dx = a.dx; P.dout = a.dout; P.bs_dx = a.bs_dx; P.bs_do = a.bs_do;
-  P.res = a.residual ? 1.f : 0.f; P.wv_part = wv_part;
-  const int threads = 32 + p.cons_threads;
-#define MRLA_TMA_LAUNCH2(CBV, BIGV, FUSEV)                                                                \
+  P.res = a.residual ? 1.f : 0.f; P.wv_part = wv_part;   // every (slot, channel) of wv_part is written by its CTA
+  const int threads = p.cons_threads;   // no producer warp: thread 0 issues the TMA traffic
+  const bool ragged = (a.W % KC) != 0;
+#define MRLA_TMA_LAUNCH3(CBV, KCV, FUSEV, RAGV)                                                           \
   {                                                                                                       \
-    auto k = k_light_nhwc_tma_bwd_ring<T, CBV, ACT, BIGV, FUSEV>;                                         \
+    auto k = k_light_nhwc_ring<T, CBV, ACT, FUSEV, RAGV, KCV>;                                            \
     e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);                \
     if (e != cudaSuccess) return (int)e;                                                                  \
-    k<<<p.grid, threads, p.smem, st>>>(tx, tdy, to, P);                                                   \
+    k<<<p.grid, threads, p.smem, st>>>(tx, tdy, to, tdx, tdo, P);                                         \
   }
-#define MRLA_TMA_LAUNCH1(CBV, BIGV)                                                                       \
+#define MRLA_TMA_LAUNCH2(CBV, KCV, FUSEV)                                                                 \
   {                                                                                                       \
-    if (a.fuse_relu_bwd) MRLA_TMA_LAUNCH2(CBV, BIGV, true) else MRLA_TMA_LAUNCH2(CBV, BIGV, false)        \
+    if (ragged) MRLA_TMA_LAUNCH3(CBV, KCV, FUSEV, true) else MRLA_TMA_LAUNCH3(CBV, KCV, FUSEV, false)     \
+  }
+#define MRLA_TMA_LAUNCH1(CBV, KCV)                                                                        \
+  {                                                                                                       \
+    if (a.fuse_relu_bwd) MRLA_TMA_LAUNCH2(CBV, KCV, true) else MRLA_TMA_LAUNCH2(CBV, KCV, false)          \
   }
 #define MRLA_TMA_LAUNCH(CBV)                                                                              \
   {                                                                                                       \
-    if (p.big) MRLA_TMA_LAUNCH1(CBV, true) else MRLA_TMA_LAUNCH1(CBV, false)                              \
+    if (p.big) MRLA_TMA_LAUNCH1(CBV, 8) else MRLA_TMA_LAUNCH1(CBV, 4)                                     \
   }
   if (p.CB == 64) MRLA_TMA_LAUNCH(64)
   else if (p.CB == 128) MRLA_TMA_LAUNCH(128)
@@ -333,6 +349,7 @@ int launch_tma_bwd_ring(const MrlaLightArgs& a, cudaStream_t st, const TmaBwdPla
 #undef MRLA_TMA_LAUNCH
 #undef MRLA_TMA_LAUNCH1
 #undef MRLA_TMA_LAUNCH2
+#undef MRLA_TMA_LAUNCH3
   MRLA_CHECK_LAUNCH();
   return MRLA_OK;
 }
@@ -343,7 +360,8 @@ inline bool light_bwd_can_fuse_relu(const MrlaLightArgs& a) {
   const int es = a.dtype == MRLA_F32 ? 4 : 2;
   TmaBwdPlan tpb, tpr;
   return tma_ptr_ok(a.x, a.bs_x, es) && tma_ptr_ok(a.o, a.bs_o, es) && tma_ptr_ok(a.dy, a.bs_dy, es) &&
-         (a.bs_dx * es) % 4 == 0 && (a.bs_do * es) % 4 == 0 && make_tma_bwd_plan(a, &tpb) && make_tma_ring_plan(a, &tpr);
+         tma_ptr_ok(a.dx, a.bs_dx, es) && tma_ptr_ok(a.dout, a.bs_do, es) && make_tma_bwd_plan(a, &tpb) &&
+         make_tma_ring_plan(a, &tpr);
 }
 
 // ------------------------------------------------------------------------------------ forward
@@ -444,7 +462,7 @@ int light_backward_impl(const MrlaLightArgs& a, cudaStream_t st) {
                      tma_ptr_ok(a.dy, a.bs_dy, es_) && (a.bs_dx * es_) % 4 == 0 && (a.bs_do * es_) % 4 == 0 &&
                      make_tma_bwd_plan(a, &tpb);
   TmaBwdPlan tpr;
-  const bool tma_r = tma_b && make_tma_ring_plan(a, &tpr);
+  const bool tma_r = tma_b && tma_ptr_ok(a.dx, a.bs_dx, es_) && tma_ptr_ok(a.dout, a.bs_do, es_) && make_tma_ring_plan(a, &tpr);
   if (a.fuse_relu_bwd && !tma_r) return MRLA_ERR_UNSUPPORTED;   // callers ask mrla_light_bwd_fuses_relu() first
   const int nparts = tma_r ? tpr.maxslots : (tma_b ? tpb.maxslots : pb.grid_y);
   const size_t need = ((size_t)nparts * a.C * 9 + (size_t)a.B * 2 * a.k_size) * sizeof(float);

@@ -23,6 +23,7 @@ struct TmaSweepParams {
   int B, C, H, W;
   int G, S, NQ, ncb, items;
   int cons_threads;
+  int rev;              // 1: walk the batch from the last sample down (the previous sweep left that end in L2)
   uint32_t x_bytes, o_bytes, stage_bytes;   // per stage (x tile, o/dy tile, total)
   const float* wv;      // [C,9]
   float* mom;           // MODE 0: [6,B,C] ; MODE 2: gmom [3,B,C]
@@ -185,7 +186,8 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       int st = 0;
       uint32_t ph = 1;  // first pass over the ring: slots are free
       for (int item = blockIdx.x; item < P.items; item += gridDim.x) {
-        const int b = item / P.ncb, cb = item - b * P.ncb;
+        const int b0 = item / P.ncb, cb = item - b0 * P.ncb;
+        const int b = P.rev ? P.B - 1 - b0 : b0;
         for (int g = 0; g < ngroups; ++g) {
           mbar_wait(&empty[st], ph);
           unsigned char* sx = stages + (size_t)st * P.stage_bytes;
@@ -233,7 +235,8 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   int red_sel = 0;   // double-buffered reduction scratch: one consumer barrier per image
 
   for (int item = blockIdx.x; item < P.items; item += gridDim.x) {
-    const int b = item / P.ncb, cb = item - b * P.ncb;
+    const int b0 = item / P.ncb, cb = item - b0 * P.ncb;
+    const int b = P.rev ? P.B - 1 - b0 : b0;
     const int c = cb * CB + 2 * p;
     const bool chan_ok = c < P.C;
     if (cb != cur_cb) {
@@ -437,6 +440,7 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 struct TmaBwdParams {
   int B, C, H, W;
   int G, S, NQ, ncb, NT, WT, items, ipc, cons_threads, maxslots;
+  int cpc;             // ring kernel: CTAs per channel block (grid = ncb * cpc)
   uint32_t x_bytes, t_bytes, stage_bytes;
   const float* wv;
   const float* lam;
@@ -707,311 +711,6 @@ k_light_nhwc_tma_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
               if (++st_cur == P.S) { st_cur = 0; ph_cur ^= 1; }
             }
           }
-        }
-      }
-    }
-  }
-  if (cur_cb >= 0) flush_dw(cur_cb);
-}
-
-// =====================================================================================================
-// v3 sweep B: T rows travel through a 4-slot shared-memory ring instead of being recomputed on halo columns.
-// Same tiles as sweep A (x with one halo column, dy, o), 14 consumer warps per SM at W = 56 (the halo-recompute
-// kernel above needs ~210 registers and runs 7).  Per row step: compute V, T for the 4 own columns, store T[t]
-// into ring slot t%4, one consumer-wide named barrier, then dX[t-1] = res*dy + dyc + Σ wv[i][dj]*T[t-i][w-dj+1]
-// from the ring.  Work items are contiguous (cb, b) ranges so dWv stays in registers across samples.
-// BIG: one 480-thread CTA per SM (W = 56 / 28); !BIG: 160-thread CTAs, three per SM (small images)
-// FUSE: x = relu(z + o) was formed in front of the tail; the epilogue writes dz = dx_total*[x>0] into dx and the
-//       total identity gradient lam*dS + dz into dout (no separate threshold_backward / grad-accumulation pass).
-template <typename T, int CB, int ACT, bool BIG, bool FUSE>
-__global__ void __launch_bounds__(BIG ? 480 : 160, BIG ? 1 : 3)
-k_light_nhwc_tma_bwd_ring(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy,
-                          const __grid_constant__ CUtensorMap tm_o, TmaBwdParams P) {
-  constexpr int NP = CB / 2;
-  constexpr int ES = sizeof(T);
-  constexpr uint32_t CS = CB * ES;        // bytes between adjacent tile columns
-  constexpr uint32_t TS = NP * 8;         // bytes between adjacent ring columns (float2 per channel pair)
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-  uint64_t* empty = full + 16;
-  unsigned char* stages = smem_raw + 256;
-  const int ring_cols = P.NQ * kCols + 2;
-  unsigned char* ring = stages + (size_t)P.S * P.stage_bytes;          // [4][ring_cols][NP] float2
-  float2* red = reinterpret_cast<float2*>(ring);                        // aliases the ring between channel blocks
-  const uint32_t ring_slot_bytes = (uint32_t)ring_cols * TS;
-  const int ncw = P.cons_threads / 32;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < P.S; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], ncw);
-    }
-    mbar_fence_init();
-  }
-  __syncthreads();
-  const int ngroups = (P.H + P.G - 1) / P.G;
-  const int item_beg = blockIdx.x * P.ipc;
-  const int item_end = min(item_beg + P.ipc, P.items);
-
-  if (threadIdx.x < 32) {
-    if (threadIdx.x == 0) {
-      tma_prefetch_desc(&tm_x);
-      tma_prefetch_desc(&tm_dy);
-      tma_prefetch_desc(&tm_o);
-      int st = 0;
-      uint32_t ph = 1;
-      for (int item = item_beg; item < item_end; ++item) {
-        const int cb = item / P.B, b = item - cb * P.B;
-        for (int g = 0; g < ngroups; ++g) {
-          mbar_wait(&empty[st], ph);
-          unsigned char* sx = stages + (size_t)st * P.stage_bytes;
-          mbar_arrive_expect_tx(&full[st], P.stage_bytes);
-          tma_load_4d(sx, &tm_x, &full[st], cb * CB, -1, g * P.G, b);
-          tma_load_4d(sx + P.x_bytes, &tm_dy, &full[st], cb * CB, 0, g * P.G, b);
-          tma_load_4d(sx + P.x_bytes + P.t_bytes, &tm_o, &full[st], cb * CB, 0, g * P.G, b);
-          if (++st == P.S) { st = 0; ph ^= 1; }
-        }
-      }
-    }
-    return;
-  }
-
-  const int ct = threadIdx.x - 32;
-  const int p = ct % NP, q = ct / NP;
-  const int lane = threadIdx.x & 31;
-  const uint32_t stages_s = smem_u32(stages);
-  const uint32_t ring_s = smem_u32(ring);
-  const uint32_t xrow_bytes = (uint32_t)(P.NQ * kCols + 2) * CS;
-  const uint32_t trow_bytes = (uint32_t)(P.NQ * kCols) * CS;
-  const uint32_t tbase = (uint32_t)(q * kCols) * CS + (uint32_t)p * 2 * ES;
-  const uint32_t rbase = ring_s + (uint32_t)(q * kCols) * TS + (uint32_t)p * 8;   // ring column = image column + 1
-  const bool ragged = (P.W % kCols) != 0;
-  bool cvalid[kCols];
-#pragma unroll
-  for (int j = 0; j < kCols; ++j) cvalid[j] = (q * kCols + j) < P.W;
-  // zero the two ring columns nobody writes (image columns -1 and 4*NQ)
-  if (q == 0) {
-    for (int sl = 0; sl < 4; ++sl) {
-      asm volatile("st.shared.v2.f32 [%0], {%1,%1};" ::"r"(ring_s + sl * ring_slot_bytes + (uint32_t)p * 8), "f"(0.f));
-      asm volatile("st.shared.v2.f32 [%0], {%1,%1};" ::"r"(ring_s + sl * ring_slot_bytes +
-                                                          (uint32_t)(ring_cols - 1) * TS + (uint32_t)p * 8), "f"(0.f));
-    }
-  }
-  named_bar_sync(1, P.cons_threads);
-
-  int st_cur = 0;
-  uint32_t ph_cur = 0;
-  int rr = 0;
-  uint32_t xa = stages_s + tbase;                 // address of x row r
-  uint32_t ta_ = stages_s + P.x_bytes + tbase;    // address of dy row r (o row = + t_bytes)
-  int cur_cb = -1;
-  float2 dw[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) dw[i] = f2(0.f, 0.f);
-  float2 w9[9];
-  float2 lm = f2(0.f, 0.f);
-  const int64_t BC = (int64_t)P.B * P.C;
-  const int64_t row_stride = (int64_t)P.W * P.C;
-
-  auto flush_dw = [&](int cb) {
-    named_bar_sync(1, P.cons_threads);  // every thread is done with the ring
-#pragma unroll
-    for (int i = 0; i < 9; ++i) red[((size_t)q * 9 + i) * NP + p] = dw[i];
-    named_bar_sync(1, P.cons_threads);
-    const int first_cta = (cb * P.B) / P.ipc;
-    const int slot = blockIdx.x - first_cta;
-    for (int idx = ct; idx < 9 * NP; idx += P.cons_threads) {
-      const int tap = idx / NP, pp = idx - tap * NP;
-      float2 s = f2(0.f, 0.f);
-      for (int qq = 0; qq < P.NQ; ++qq) {
-        const float2 v = red[((size_t)qq * 9 + tap) * NP + pp];
-        s.x += v.x;
-        s.y += v.y;
-      }
-      const int cc = cb * CB + 2 * pp;
-      if (cc < P.C) {
-        float* dst = P.wv_part + ((int64_t)slot * P.C + cc) * 9 + tap;
-        dst[0] = s.x;
-        dst[9] = s.y;
-      }
-    }
-    named_bar_sync(1, P.cons_threads);
-    // restore the zero halo columns the partials overwrote
-    if (q == 0) {
-      for (int sl = 0; sl < 4; ++sl) {
-        asm volatile("st.shared.v2.f32 [%0], {%1,%1};" ::"r"(ring_s + sl * ring_slot_bytes + (uint32_t)p * 8), "f"(0.f));
-        asm volatile("st.shared.v2.f32 [%0], {%1,%1};" ::"r"(ring_s + sl * ring_slot_bytes +
-                                                            (uint32_t)(ring_cols - 1) * TS + (uint32_t)p * 8), "f"(0.f));
-      }
-    }
-    named_bar_sync(1, P.cons_threads);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) dw[i] = f2(0.f, 0.f);
-  };
-
-  for (int item = item_beg; item < item_end; ++item) {
-    const int cb = item / P.B, b = item - cb * P.B;
-    const int c = cb * CB + 2 * p;
-    const bool chan_ok = c < P.C;
-    if (cb != cur_cb) {
-      if (cur_cb >= 0) flush_dw(cur_cb);
-      cur_cb = cb;
-#pragma unroll
-      for (int i = 0; i < 9; ++i)
-        w9[i] = chan_ok ? f2(P.wv[(int64_t)c * 9 + i], P.wv[(int64_t)(c + 1) * 9 + i]) : f2(0.f, 0.f);
-      lm = (chan_ok && P.lam) ? f2(P.lam[c], P.lam[c + 1]) : f2(0.f, 0.f);
-    }
-    float2 q0 = f2(0.f, 0.f), q1 = q0, q2 = q0, q3 = q0, ta = q0, dyc = q0;
-    if (chan_ok) {
-      const float* cp = P.bcoef + (int64_t)b * P.C + c;
-      q0 = *reinterpret_cast<const float2*>(cp);
-      q1 = *reinterpret_cast<const float2*>(cp + BC);
-      q2 = *reinterpret_cast<const float2*>(cp + 2 * BC);
-      q3 = *reinterpret_cast<const float2*>(cp + 3 * BC);
-      ta = *reinterpret_cast<const float2*>(cp + 4 * BC);
-      dyc = *reinterpret_cast<const float2*>(cp + 5 * BC);
-    }
-    const float2 res2 = f2(P.res, P.res);
-    // running row pointers: dop -> row t of dO, dxp -> row h = t-1 of dX
-    T* dop = static_cast<T*>(P.dout) + (int64_t)b * P.bs_do + (int64_t)(q * kCols) * P.C + c;
-    T* dxp = static_cast<T*>(P.dx) + (int64_t)b * P.bs_dx + (int64_t)(q * kCols) * P.C + c;
-
-    float2 xw[3][kWin];
-    float2 dyprev[kCols];
-#pragma unroll
-    for (int k = 0; k < kWin; ++k) xw[2][k] = f2(0.f, 0.f);
-#pragma unroll
-    for (int j = 0; j < kCols; ++j) dyprev[j] = f2(0.f, 0.f);
-    // FUSE: lam*dS of the previous T row, kept in storage precision (one register per pair) until its dX row is
-    // emitted one step later
-    typename RawPair<T>::type doprev[FUSE ? kCols : 1], docur[FUSE ? kCols : 1];
-#pragma unroll
-    for (int j = 0; j < (FUSE ? kCols : 1); ++j) doprev[j] = pack_pair<T>(f2(0.f, 0.f));
-    bool sv[kCols];
-#pragma unroll
-    for (int j = 0; j < kCols; ++j) sv[j] = chan_ok && cvalid[j];
-    uint32_t t_prev = 0;
-    int rel_stage = -1;
-    for (int r0 = 0; r0 <= P.H + 1; r0 += 3) {
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int r = r0 + i;
-        if (r <= P.H + 1) {
-          uint32_t t_this = 0;
-          int rel_next = -1;
-          // ---- fetch x row r ----
-          if (r < P.H) {
-            if (rr == 0) mbar_wait(&full[st_cur], ph_cur);
-#pragma unroll
-            for (int k = 0; k < kWin; ++k) xw[i][k] = lds_pair<T>(xa + k * CS);
-            t_this = ta_;
-            xa += xrow_bytes;
-            ta_ += trow_bytes;
-            if (++rr == P.G || r == P.H - 1) {
-              rel_next = st_cur;
-              rr = 0;
-              if (++st_cur == P.S) { st_cur = 0; ph_cur ^= 1; }
-              xa = stages_s + (uint32_t)st_cur * P.stage_bytes + tbase;
-              ta_ = xa + P.x_bytes;
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < kWin; ++k) xw[i][k] = f2(0.f, 0.f);
-          }
-          float2 dycur[kCols];
-#pragma unroll
-          for (int j = 0; j < kCols; ++j) dycur[j] = f2(0.f, 0.f);
-#pragma unroll
-          for (int j = 0; j < (FUSE ? kCols : 1); ++j) docur[j] = pack_pair<T>(f2(0.f, 0.f));
-          // ---- T row t = r-1 ----
-          if (r >= 1 && r <= P.H) {
-            const int t = r - 1;
-            const uint32_t tb = t_prev;
-            const float2(&top)[kWin] = xw[(i + 1) % 3];
-            const float2(&mid)[kWin] = xw[(i + 2) % 3];
-            const float2(&bot)[kWin] = xw[i];
-            float2 u4[kCols];
-            conv9x4(top, mid, bot, w9, u4);
-            const uint32_t rslot = rbase + (uint32_t)(t & 3) * ring_slot_bytes + TS;  // +1 column: ring col = image col + 1
-#pragma unroll
-            for (int j = 0; j < kCols; ++j) {
-              const float2 v = act2<ACT>(u4[j]);
-              const float2 gy = lds_pair<T>(tb + j * CS);
-              const float2 ov = lds_pair<T>(tb + P.t_bytes + j * CS);
-              float2 ds = ffma2(q1, gy, q0);
-              ds = ffma2(q2, v, ds);
-              ds = ffma2(q3, ov, ds);
-              float2 tt = fmul2(ta, ds);
-              if (ACT == 1) tt = fmul2(tt, f2(act_grad<1>(u4[j].x), act_grad<1>(u4[j].y)));
-              if (ragged && !cvalid[j]) tt = f2(0.f, 0.f);
-              dycur[j] = gy;
-              asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(rslot + j * TS), "f"(tt.x), "f"(tt.y) : "memory");
-              if (FUSE) docur[j] = pack_pair<T>(fmul2(lm, ds));
-              else if (sv[j]) stg_pair<T>(dop + j * P.C, fmul2(lm, ds));
-              dw[0] = ffma2(tt, top[j], dw[0]);
-              dw[1] = ffma2(tt, top[j + 1], dw[1]);
-              dw[2] = ffma2(tt, top[j + 2], dw[2]);
-              dw[3] = ffma2(tt, mid[j], dw[3]);
-              dw[4] = ffma2(tt, mid[j + 1], dw[4]);
-              dw[5] = ffma2(tt, mid[j + 2], dw[5]);
-              dw[6] = ffma2(tt, bot[j], dw[6]);
-              dw[7] = ffma2(tt, bot[j + 1], dw[7]);
-              dw[8] = ffma2(tt, bot[j + 2], dw[8]);
-            }
-            if (!FUSE) dop += row_stride;
-            if (rel_stage >= 0) {
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&empty[rel_stage]);
-            }
-          }
-          t_prev = t_this;
-          rel_stage = rel_next;
-          named_bar_sync(1, P.cons_threads);
-          // ---- dX row h = r-2 from T rows r-3, r-2, r-1 ----
-          if (r >= 2) {
-            float2 acc[kCols];
-#pragma unroll
-            for (int j = 0; j < kCols; ++j) acc[j] = ffma2(res2, dyprev[j], dyc);
-#pragma unroll
-            for (int ii = 0; ii < 3; ++ii) {
-              const int tr = r - 1 - ii;  // T row feeding tap row ii
-              if (tr >= 0 && tr < P.H) {
-                const uint32_t rs = rbase + (uint32_t)(tr & 3) * ring_slot_bytes;  // ring col of image col 4q-1
-                float2 tw[kWin];
-#pragma unroll
-                for (int k = 0; k < kWin; ++k)
-                  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(tw[k].x), "=f"(tw[k].y) : "r"(rs + k * TS));
-                // dX[h][w] += wv[ii][dj] * T[tr][w - dj + 1]   (tw[k] holds image column 4q-1+k)
-#pragma unroll
-                for (int j = 0; j < kCols; ++j) {
-                  acc[j] = ffma2(w9[ii * 3 + 0], tw[j + 2], acc[j]);
-                  acc[j] = ffma2(w9[ii * 3 + 1], tw[j + 1], acc[j]);
-                  acc[j] = ffma2(w9[ii * 3 + 2], tw[j], acc[j]);
-                }
-              }
-            }
-            if (FUSE) {
-              const float2(&xrow)[kWin] = xw[(i + 1) % 3];   // x row h = r-2
-#pragma unroll
-              for (int j = 0; j < kCols; ++j) {
-                const float2 xc = xrow[j + 1];
-                const float2 dz = f2(xc.x > 0.f ? acc[j].x : 0.f, xc.y > 0.f ? acc[j].y : 0.f);
-                if (sv[j]) {
-                  stg_pair<T>(dxp + j * P.C, dz);
-                  stg_pair<T>(dop + j * P.C, fadd2(unpack_pair<T>(doprev[j]), dz));   // total identity gradient
-                }
-              }
-              dop += row_stride;
-            } else {
-#pragma unroll
-              for (int j = 0; j < kCols; ++j)
-                if (sv[j]) stg_pair<T>(dxp + j * P.C, acc[j]);
-            }
-            dxp += row_stride;
-          }
-#pragma unroll
-          for (int j = 0; j < kCols; ++j) dyprev[j] = dycur[j];
-#pragma unroll
-          for (int j = 0; j < (FUSE ? kCols : 1); ++j) doprev[j] = docur[j];
         }
       }
     }

@@ -90,3 +90,25 @@ def test_check_error_messages():
     with pytest.raises(RuntimeError, match="CUDA error 700"):
         _lib.check(700, "x")
     _lib.check(0, "x")
+
+
+# Shapes of BASELINE.json's configs (ResNet-50 stages at B=256 bf16, the fp32 small stages, DeiT-tiny's 14x14 token
+# image, EfficientNet-B0's late stages): the folded backward (ReLU mask + total identity gradient inside sweep B) must
+# be served by the ring kernel, never by the two-library-op fallback of ops.py.  The query only does plan arithmetic
+# (no CUDA call), so it runs on CPU.  (fp32 at 56x56 / 28x28 and C < 64 at W > 16 do fall back: tiles too large /
+# channel blocks too empty; those are parity-test shapes, not bench shapes.)
+@pytest.mark.parametrize("C,HW,dt", [(256, 56, "BF16"), (512, 28, "BF16"), (1024, 14, "BF16"), (2048, 7, "BF16"),
+                                     (256, 56, "F16"), (1024, 14, "F32"), (2048, 7, "F32"), (192, 14, "BF16"),
+                                     (80, 14, "BF16"), (112, 14, "BF16"), (192, 7, "BF16"), (320, 7, "BF16")])
+def test_ring_kernel_serves_the_baseline_shapes(C, HW, dt):
+    L = _lib.lib()
+    a = _lib.MrlaLightArgs()
+    a.B, a.C, a.H, a.W, a.dim_perhead, a.k_size = 256, C, HW, HW, 8, 5
+    a.dtype, a.layout, a.bn_mode = getattr(_lib, dt), _lib.NHWC, _lib.BN_TRAIN
+    n = C * HW * HW
+    a.bs_x = a.bs_o = a.bs_dy = a.bs_dx = a.bs_do = n
+    fake = 0x10000  # 16-byte aligned, never dereferenced
+    for f in ("x", "o", "dy", "dx", "dout"):
+        setattr(a, f, fake)
+    assert L.mrla_light_bwd_fuses_relu(ctypes.byref(a)) == 1
+    assert L.mrla_light_bwd_scratch_bytes(ctypes.byref(a)) > 0
