@@ -429,7 +429,7 @@ int light_forward_impl(const MrlaLightArgs& a, cudaStream_t st) {
     int th = round_up(a.C < 1024 ? a.C : 1024, 32);
     k_light_gate<<<a.B, th, 2 * a.C * sizeof(float), st>>>(a.mom, a.wq, a.wk, a.gate, ms);
     MRLA_CHECK_LAUNCH();
-    k_light_bn_coef<<<(a.C + 31) / 32, 1024, 0, st>>>(a.mom, a.gate, a.lam, a.gamma, a.beta, a.running_mean,
+    k_light_bn_coef<<<(a.C + kMidCPB - 1) / kMidCPB, kMidCPB * kMidBL, 0, st>>>(a.mom, a.gate, a.lam, a.gamma, a.beta, a.running_mean,
                                                        a.running_var, a.drop_scale, a.mean, a.rstd, a.coef, ms);
     MRLA_CHECK_LAUNCH();
   }
@@ -496,7 +496,7 @@ int light_backward_impl(const MrlaLightArgs& a, cudaStream_t st) {
   // mid
   MidShape ms = mid_shape(a, full);
   {
-    k_light_bwd_chan<<<(a.C + 31) / 32, 1024, 0, st>>>(a.mom, a.gmom, a.gate, a.lam, a.gamma, a.drop_scale, a.mean,
+    k_light_bwd_chan<<<(a.C + kMidCPB - 1) / kMidCPB, kMidCPB * kMidBL, 0, st>>>(a.mom, a.gmom, a.gate, a.lam, a.gamma, a.drop_scale, a.mean,
                                                         a.rstd, a.bcoef, a.dlam, a.dgamma, a.dbeta, ms);
     MRLA_CHECK_LAUNCH();
     int th = round_up(a.C < 1024 ? a.C : 1024, 32);

@@ -50,7 +50,27 @@ static __global__ void __launch_bounds__(1024) k_light_gate(const float* __restr
   }
 }
 
-// ------------------------------------------------- BN statistics + forward coefficients (32 channels / CTA)
+// Tiling of the per-channel kernels: kMidCPB channels x kMidBL batch lanes per 1024-thread CTA.  A warp holds 4 batch
+// lanes of the 8 channels (32-byte coalesced segments of the [B,C] side tensors); sums over the batch go through two
+// shuffles, one shared-memory slot per warp and a 32-term serial tail — C/8 CTAs instead of C/32, B/128 dependent
+// iterations per thread instead of B/32.
+constexpr int kMidCPB = 8;
+constexpr int kMidBL = 128;
+
+// sum `v` over all threads of the CTA that share channel lane `cl` (threadIdx.x & 7); result valid where bl == 0
+__device__ __forceinline__ double mid_channel_sum(double v, double (*red)[kMidCPB], int cl, int bl) {
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  __syncthreads();                                  // previous use of `red` is over
+  if ((threadIdx.x & 31) < kMidCPB) red[threadIdx.x >> 5][cl] = v;
+  __syncthreads();
+  double a = 0.0;
+  if (bl == 0)
+    for (int j = 0; j < 32; ++j) a += red[j][cl];
+  return a;
+}
+
+// ------------------------------------------------- BN statistics + forward coefficients (8 channels / CTA)
 // mean_c = Σ_b (a ΣV + λ Σo)/n ; E[s²]_c = Σ_b (a² ΣV² + 2aλ ΣVo + λ² Σo²)/n  (accumulated in fp64)
 // coef = [3,B,C]:  A = m_b γ r a ,  L = m_b γ r λ ,  D = m_b (β − γ r μ)
 static __global__ void __launch_bounds__(1024) k_light_bn_coef(const float* __restrict__ mom, const float* __restrict__ gate,
@@ -59,11 +79,10 @@ static __global__ void __launch_bounds__(1024) k_light_bn_coef(const float* __re
                                                         float* __restrict__ running_var,
                                                         const float* __restrict__ drop_scale, float* __restrict__ mean,
                                                         float* __restrict__ rstd, float* __restrict__ coef, MidShape s) {
-  __shared__ double red1[32][33];
-  __shared__ double red2[32][33];
-  __shared__ float s_mu[32], s_r[32];
-  const int cl = threadIdx.x & 31, bl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
+  __shared__ double red[32][kMidCPB];
+  __shared__ float s_mu[kMidCPB], s_r[kMidCPB];
+  const int cl = threadIdx.x & (kMidCPB - 1), bl = threadIdx.x / kMidCPB;
+  const int c = blockIdx.x * kMidCPB + cl;
   const bool cok = c < s.C;
   const int g = s.C / s.d;
   const int64_t BC = (int64_t)s.B * s.C;
@@ -73,8 +92,8 @@ static __global__ void __launch_bounds__(1024) k_light_bn_coef(const float* __re
   if (s.bn_mode == 1) {
     double s1 = 0.0, s2 = 0.0;
     if (cok) {
-#pragma unroll 4
-      for (int b = bl; b < s.B; b += 32) {
+#pragma unroll 2
+      for (int b = bl; b < s.B; b += kMidBL) {
         const int64_t i = (int64_t)b * s.C + c;
         const double a = gate[(int64_t)b * g + c / s.d];
         const double sv = mom[BC + i], svv = mom[2 * BC + i];
@@ -88,12 +107,9 @@ static __global__ void __launch_bounds__(1024) k_light_bn_coef(const float* __re
         s2 += t2;
       }
     }
-    red1[bl][cl] = s1;
-    red2[bl][cl] = s2;
-    __syncthreads();
+    const double a1 = mid_channel_sum(s1, red, cl, bl);
+    const double a2 = mid_channel_sum(s2, red, cl, bl);
     if (bl == 0) {
-      double a1 = 0.0, a2 = 0.0;
-      for (int j = 0; j < 32; ++j) { a1 += red1[j][cl]; a2 += red2[j][cl]; }
       const double mu = a1 / n;
       double var = a2 / n - mu * mu;
       if (var < 0.0) var = 0.0;
@@ -129,7 +145,7 @@ static __global__ void __launch_bounds__(1024) k_light_bn_coef(const float* __re
   const float be = (s.bn_mode != 0) ? beta[c] : 0.f;
   const float gr = ga * s_r[cl];
   const float dterm = be - gr * s_mu[cl];
-  for (int b = bl; b < s.B; b += 32) {
+  for (int b = bl; b < s.B; b += kMidBL) {
     const int64_t i = (int64_t)b * s.C + c;
     const float mb = drop_scale ? drop_scale[b] : 1.f;
     const float a = gate[(int64_t)b * g + c / s.d];
@@ -139,7 +155,7 @@ static __global__ void __launch_bounds__(1024) k_light_bn_coef(const float* __re
   }
 }
 
-// ------------------------------------------------------- backward, per-channel part (32 channels / CTA)
+// ------------------------------------------------------- backward, per-channel part (8 channels / CTA)
 // G' = m_b dY.  dβ = Σ_b ΣG' ; dγ = r Σ_b (a ΣG'V + λ ΣG'o − μ ΣG') ; m1 = dβ/n ; m2 = dγ/n  (train only)
 // dλ = γ r Σ_b (ΣG'o − m1 Σo − m2 ΣŜo) ; da[b,c] = γ r (ΣG'V − m1 ΣV − m2 ΣŜV)
 // bcoef = [7,B,C]: Q0,Q1,Q2,Q3, Ta, dyc (filled by k_light_bwd_gate), da[b,c]
@@ -151,11 +167,10 @@ static __global__ void __launch_bounds__(1024) k_light_bwd_chan(const float* __r
                                                          float* __restrict__ bcoef, float* __restrict__ dlam,
                                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                          MidShape s) {
-  __shared__ double red1[32][33];
-  __shared__ double red2[32][33];
-  __shared__ double s_m1[32], s_m2[32];
-  const int cl = threadIdx.x & 31, bl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
+  __shared__ double red[32][kMidCPB];
+  __shared__ double s_m1[kMidCPB], s_m2[kMidCPB];
+  const int cl = threadIdx.x & (kMidCPB - 1), bl = threadIdx.x / kMidCPB;
+  const int c = blockIdx.x * kMidCPB + cl;
   const bool cok = c < s.C;
   const int g = s.C / s.d;
   const int64_t BC = (int64_t)s.B * s.C;
@@ -168,8 +183,8 @@ static __global__ void __launch_bounds__(1024) k_light_bwd_chan(const float* __r
   // pass 1: dβ, dγ
   double s1 = 0.0, s2 = 0.0;
   if (cok && s.bn_mode != 0) {
-#pragma unroll 4
-    for (int b = bl; b < s.B; b += 32) {
+#pragma unroll 2
+    for (int b = bl; b < s.B; b += kMidBL) {
       const int64_t i = (int64_t)b * s.C + c;
       const double mb = drop_scale ? (double)drop_scale[b] : 1.0;
       const double a = gate[(int64_t)b * g + c / s.d];
@@ -179,12 +194,9 @@ static __global__ void __launch_bounds__(1024) k_light_bwd_chan(const float* __r
       s2 += a * gv + lm * go - mu * g1;
     }
   }
-  red1[bl][cl] = s1;
-  red2[bl][cl] = s2;
-  __syncthreads();
+  const double a1 = mid_channel_sum(s1, red, cl, bl);
+  double a2 = mid_channel_sum(s2, red, cl, bl);
   if (bl == 0) {
-    double a1 = 0.0, a2 = 0.0;
-    for (int j = 0; j < 32; ++j) { a1 += red1[j][cl]; a2 += red2[j][cl]; }
     a2 *= r;
     if (cok && s.bn_mode != 0) {
       if (dbeta) dbeta[c] = (float)a1;
@@ -201,8 +213,8 @@ static __global__ void __launch_bounds__(1024) k_light_bwd_chan(const float* __r
   // pass 2: dλ, da[b,c], sweep-B coefficients
   double sl = 0.0;
   if (cok) {
-#pragma unroll 4
-    for (int b = bl; b < s.B; b += 32) {
+#pragma unroll 2
+    for (int b = bl; b < s.B; b += kMidBL) {
       const int64_t i = (int64_t)b * s.C + c;
       const double mb = drop_scale ? (double)drop_scale[b] : 1.0;
       const double a = gate[(int64_t)b * g + c / s.d];
@@ -228,14 +240,8 @@ static __global__ void __launch_bounds__(1024) k_light_bwd_chan(const float* __r
     }
   }
   if (dlam != nullptr) {
-    __syncthreads();
-    red1[bl][cl] = sl;
-    __syncthreads();
-    if (bl == 0 && cok) {
-      double a1 = 0.0;
-      for (int j = 0; j < 32; ++j) a1 += red1[j][cl];
-      dlam[c] = (float)a1;
-    }
+    const double al = mid_channel_sum(sl, red, cl, bl);
+    if (bl == 0 && cok) dlam[c] = (float)al;
   }
 }
 

@@ -26,34 +26,6 @@
 
 namespace mrla {
 
-template <typename T> __device__ __forceinline__ typename RawPair<T>::type lds_raw(uint32_t saddr);
-template <> __device__ __forceinline__ uint32_t lds_raw<__nv_bfloat16>(uint32_t saddr) {
-  uint32_t u;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(saddr));
-  return u;
-}
-template <> __device__ __forceinline__ uint32_t lds_raw<__half>(uint32_t saddr) {
-  uint32_t u;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(saddr));
-  return u;
-}
-template <> __device__ __forceinline__ float2 lds_raw<float>(uint32_t saddr) { return lds_pair<float>(saddr); }
-
-template <typename T> __device__ __forceinline__ typename RawPair<T>::type raw_add(typename RawPair<T>::type a,
-                                                                                  typename RawPair<T>::type b);
-template <> __device__ __forceinline__ uint32_t raw_add<__nv_bfloat16>(uint32_t a, uint32_t b) {
-  const __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
-  return *reinterpret_cast<const uint32_t*>(&r);
-}
-template <> __device__ __forceinline__ uint32_t raw_add<__half>(uint32_t a, uint32_t b) {
-  const __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
-  return *reinterpret_cast<const uint32_t*>(&r);
-}
-template <> __device__ __forceinline__ float2 raw_add<float>(float2 a, float2 b) { return fadd2(a, b); }
-
-template <typename T> __device__ __forceinline__ void stg_raw(T* p, typename RawPair<T>::type r) {
-  *reinterpret_cast<typename RawPair<T>::type*>(p) = r;
-}
 __device__ __forceinline__ void sts_v4(uint32_t saddr, float2 a, float2 b) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
 }

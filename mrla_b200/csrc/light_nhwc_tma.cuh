@@ -103,6 +103,48 @@ template <> __device__ __forceinline__ float2 unpack_pair<__half>(uint32_t u) {
 }
 template <> __device__ __forceinline__ float2 unpack_pair<float>(float2 v) { return v; }
 
+template <typename T> __device__ __forceinline__ typename RawPair<T>::type lds_raw(uint32_t saddr);
+template <> __device__ __forceinline__ uint32_t lds_raw<__nv_bfloat16>(uint32_t saddr) {
+  uint32_t u;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(saddr));
+  return u;
+}
+template <> __device__ __forceinline__ uint32_t lds_raw<__half>(uint32_t saddr) {
+  uint32_t u;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(saddr));
+  return u;
+}
+template <> __device__ __forceinline__ float2 lds_raw<float>(uint32_t saddr) { return lds_pair<float>(saddr); }
+
+template <typename T> __device__ __forceinline__ typename RawPair<T>::type raw_add(typename RawPair<T>::type a,
+                                                                                  typename RawPair<T>::type b);
+template <> __device__ __forceinline__ uint32_t raw_add<__nv_bfloat16>(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+template <> __device__ __forceinline__ uint32_t raw_add<__half>(uint32_t a, uint32_t b) {
+  const __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+template <> __device__ __forceinline__ float2 raw_add<float>(float2 a, float2 b) { return fadd2(a, b); }
+
+template <typename T> __device__ __forceinline__ void stg_raw(T* p, typename RawPair<T>::type r) {
+  *reinterpret_cast<typename RawPair<T>::type*>(p) = r;
+}
+// relu on a pair in storage precision
+template <typename T> __device__ __forceinline__ typename RawPair<T>::type raw_relu(typename RawPair<T>::type a);
+template <> __device__ __forceinline__ uint32_t raw_relu<__nv_bfloat16>(uint32_t a) {
+  const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), z);
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+template <> __device__ __forceinline__ uint32_t raw_relu<__half>(uint32_t a) {
+  const __half2 z = __floats2half2_rn(0.f, 0.f);
+  const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), z);
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+template <> __device__ __forceinline__ float2 raw_relu<float>(float2 a) { return make_float2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f)); }
+
 template <int ACT> __device__ __forceinline__ float2 act2(float2 u) {
   if (ACT == 1) return make_float2(act_fwd<1>(u.x), act_fwd<1>(u.y));
   return u;
@@ -285,19 +327,22 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           // ---- fetch x row r into window slot i ----
           if (r < P.H) {
             if (rr == 0) mbar_wait(&full[st_cur], ph_cur);
-#pragma unroll
-            for (int j = 0; j < kWin; ++j) win[i][j] = lds_pair<T>(xa + j * CS);
             if (XFOLD) {
-              // x = relu(z + identity) on the whole window (halo columns are 0 + 0), stored for the own columns
+              // x = relu(z + identity) on the whole window (halo columns are 0 + 0), formed in storage precision like
+              // the reference's in-place `out += identity; relu_` (resnet_mrla_light.py:113-114) — the conv below then
+              // sees exactly the x that is stored — and written out for the own columns
 #pragma unroll
               for (int j = 0; j < kWin; ++j) {
-                const float2 t = fadd2(win[i][j], lds_pair<T>(oa + j * CS));
-                win[i][j] = f2(fmaxf(t.x, 0.f), fmaxf(t.y, 0.f));
+                const typename RawPair<T>::type xr =
+                    raw_relu<T>(raw_add<T>(lds_raw<T>(xa + j * CS), lds_raw<T>(oa + j * CS)));
+                win[i][j] = unpack_pair<T>(xr);
+                if (j >= 1 && j <= kCols)
+                  if (sv[j - 1]) stg_raw<T>(yrow + (j - 1) * P.C, xr);
               }
-#pragma unroll
-              for (int j = 0; j < kCols; ++j)
-                if (sv[j]) stg_pair<T>(yrow + j * P.C, win[i][j + 1]);
               yrow += y_row_stride;
+            } else {
+#pragma unroll
+              for (int j = 0; j < kWin; ++j) win[i][j] = lds_pair<T>(xa + j * CS);
             }
             o_this = oa;
             xa += xrow_bytes;
