@@ -2,6 +2,7 @@
 #pragma once
 #include "../../include/mrla_b200.h"
 #include "light_mid.cuh"
+#include "light_mid_cluster.cuh"
 #include "light_sweeps.cuh"
 #include "light_nhwc_tma.cuh"
 #include "light_nhwc_ring.cuh"
@@ -69,6 +70,7 @@ inline MidShape mid_shape(const MrlaLightArgs& a, bool full) {
   m.B = a.B; m.C = a.C; m.HW = a.H * a.W; m.d = a.dim_perhead; m.k = a.k_size;
   m.bn_mode = a.bn_mode; m.has_o = (a.o != nullptr); m.full_mom = full;
   m.update_running = a.update_running; m.eps = a.eps; m.momentum = a.momentum;
+  m.da_summed = 0;
   return m;
 }
 
@@ -425,7 +427,14 @@ int light_forward_impl(const MrlaLightArgs& a, cudaStream_t st) {
   }  // sweep 1 (skipped when MODE 5 produced the moments together with x)
   // mid
   MidShape ms = mid_shape(a, full);
-  {
+  if (mid_cluster_ok(a.C, a.dim_perhead, a.k_size)) {
+    // one cluster launch: gate + BN statistics + coefficients
+    cudaError_t e = launch_mid_cluster(k_light_mid_fwd, a.C, mid_cluster_ns(a.B), st, (const float*)a.mom, a.wq, a.wk, a.lam,
+                                       a.gamma, a.beta, a.running_mean, a.running_var, a.drop_scale, a.gate, a.mean, a.rstd,
+                                       a.coef, ms);
+    if (e != cudaSuccess) return (int)e;
+    MRLA_CHECK_LAUNCH();
+  } else {
     int th = round_up(a.C < 1024 ? a.C : 1024, 32);
     k_light_gate<<<a.B, th, 2 * a.C * sizeof(float), st>>>(a.mom, a.wq, a.wk, a.gate, ms);
     MRLA_CHECK_LAUNCH();
@@ -496,8 +505,16 @@ int light_backward_impl(const MrlaLightArgs& a, cudaStream_t st) {
   // mid
   MidShape ms = mid_shape(a, full);
   {
-    k_light_bwd_chan<<<(a.C + kMidCPB - 1) / kMidCPB, kMidCPB * kMidBL, 0, st>>>(a.mom, a.gmom, a.gate, a.lam, a.gamma, a.drop_scale, a.mean,
-                                                        a.rstd, a.bcoef, a.dlam, a.dgamma, a.dbeta, ms);
+    if (mid_cluster_ok(a.C, a.dim_perhead, a.k_size)) {
+      ms.da_summed = 1;
+      cudaError_t e = launch_mid_cluster(k_light_mid_bwd, a.C, mid_cluster_ns(a.B), st, (const float*)a.mom, (const float*)a.gmom,
+                                         (const float*)a.gate, a.lam, a.gamma, a.drop_scale, (const float*)a.mean,
+                                         (const float*)a.rstd, a.bcoef, a.dlam, a.dgamma, a.dbeta, ms);
+      if (e != cudaSuccess) return (int)e;
+    } else {
+      k_light_bwd_chan<<<(a.C + kMidCPB - 1) / kMidCPB, kMidCPB * kMidBL, 0, st>>>(a.mom, a.gmom, a.gate, a.lam, a.gamma, a.drop_scale, a.mean,
+                                                          a.rstd, a.bcoef, a.dlam, a.dgamma, a.dbeta, ms);
+    }
     MRLA_CHECK_LAUNCH();
     int th = round_up(a.C < 1024 ? a.C : 1024, 32);
     const size_t sm = ((size_t)5 * a.C + a.C / a.dim_perhead) * sizeof(float);

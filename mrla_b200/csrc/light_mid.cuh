@@ -14,6 +14,7 @@ struct MidShape {
   int full_mom;         // forward moments 1..5 are valid (BN train)
   int update_running;
   float eps, momentum;
+  int da_summed;        // backward: bcoef[6] already holds da summed over the head (k_light_mid_bwd)
 };
 
 // ---------------------------------------------------------------------------- gate (one CTA per b)
@@ -280,7 +281,9 @@ static __global__ void __launch_bounds__(1024) k_light_bwd_gate(const float* __r
   const float norm = rsqrtf((float)s.d);
   for (int h = threadIdx.x; h < g; h += blockDim.x) {
     float acc = 0.f;
-    for (int i = 0; i < s.d; ++i) acc += bcoef[6 * BC + (int64_t)b * s.C + h * s.d + i];
+    if (s.da_summed) acc = bcoef[6 * BC + (int64_t)b * s.C + h * s.d];
+    else
+      for (int i = 0; i < s.d; ++i) acc += bcoef[6 * BC + (int64_t)b * s.C + h * s.d + i];
     const float a = gate[(int64_t)b * g + h];
     dl[h] = acc * a * (1.f - a) * norm;
   }
