@@ -238,6 +238,16 @@ size_t mrla_bn_scratch_bytes(const MrlaBnArgs* a);
 int mrla_bn_forward(const MrlaBnArgs* a, void* stream);
 int mrla_bn_backward(const MrlaBnArgs* a, void* stream);
 
+/* 3x3 / stride 2 / pad 1 max pooling of a dense NHWC activation [B,H,W,C] -> [B,OH,OW,C], OH = (H-1)/2 + 1 (the
+ * ResNet stem's nn.MaxPool2d: resnet/models/resnet_mrla_light.py `self.maxpool`; whole-step path of bench.py only,
+ * SURVEY.md section 8f rank 3).  idx [B,OH,OW,C] bytes keeps the winning tap kh*3+kw; backward gathers from it.
+ * Replaces at::max_pool2d_with_indices / max_pool2d_with_indices_backward (same tie and NaN rules).  C % 8 == 0;
+ * pointers aligned to 8 elements. */
+int mrla_maxpool3x3s2_forward(const void* x, void* y, unsigned char* idx, int B, int C, int H, int W, int dtype,
+                              void* stream);
+int mrla_maxpool3x3s2_backward(const void* dy, const unsigned char* idx, void* dx, int B, int C, int H, int W, int dtype,
+                               void* stream);
+
 /* Number of kernel launches the last forward / backward call on this thread enqueued
  * (bench.py reports it as gpu_launches). */
 int mrla_last_launch_count(void);

@@ -76,6 +76,7 @@ EXPORTS = (
     "mrla_abi_version", "mrla_build_info", "mrla_last_launch_count", "mrla_sizeof_light_args",
     "mrla_light_bwd_scratch_bytes", "mrla_light_bwd_fuses_relu", "mrla_light_forward", "mrla_light_backward",
     "mrla_nchw_to_nhwc", "mrla_add_relu", "mrla_sizeof_base_args", "mrla_base_bwd_scratch_bytes", "mrla_base_forward", "mrla_base_backward",
+    "mrla_maxpool3x3s2_forward", "mrla_maxpool3x3s2_backward",
 )
 
 
@@ -109,6 +110,11 @@ def lib() -> ctypes.CDLL:
         L.mrla_add_relu.restype = ctypes.c_int
         L.mrla_add_relu.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                                     ctypes.c_void_p]
+        for d in ("forward", "backward"):
+            f = getattr(L, f"mrla_maxpool3x3s2_{d}")
+            f.restype = ctypes.c_int
+            f.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                          ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         L.mrla_sizeof_base_args.restype = ctypes.c_size_t
         if L.mrla_sizeof_base_args() != ctypes.sizeof(MrlaBaseArgs):
             raise RuntimeError("MrlaBaseArgs layout mismatch between _lib.py and include/mrla_b200.h")

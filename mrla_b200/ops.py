@@ -665,3 +665,56 @@ def bn_act(x, bn: "torch.nn.BatchNorm2d", relu: bool = False) -> torch.Tensor:
         y = bn(x)   # exotic buffer dtype: leave to the library
         return torch.relu(y) if relu else y
     return _BnAct.apply(x, bn.weight, bn.bias, rm, rv, use_batch, update, momentum, bn.eps, relu)
+
+
+# ===================================================================================== stem max pooling (3x3, s2, p1)
+def _max_pool_eligible(x: torch.Tensor) -> bool:
+    if not x.is_cuda or x.dtype not in _DTYPES or x.dim() != 4:
+        return False
+    B, C, H, W = x.shape
+    lay = _layout_of(x)
+    align = 32 if x.dtype == torch.float32 else 16
+    return (lay is not None and lay[0] == _lib.NHWC and lay[1] == C * H * W and C % 8 == 0 and H > 1 and W > 1
+            and x.data_ptr() % align == 0)
+
+
+class _MaxPool3x3s2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        L = _lib.lib()
+        B, C, H, W = x.shape
+        OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = torch.empty((B, OH, OW, C), dtype=x.dtype, device=x.device).permute(0, 3, 1, 2)
+        idx = torch.empty((B, OH, OW, C), dtype=torch.uint8, device=x.device)
+        _lib.check(L.mrla_maxpool3x3s2_forward(_ptr(x), _ptr(y), _ptr(idx), B, C, H, W, _DTYPES[x.dtype], _stream()),
+                   "mrla_maxpool3x3s2_forward")
+        launch_counter["fwd"] += L.mrla_last_launch_count()
+        ctx.shape = (B, C, H, W)
+        ctx.save_for_backward(idx)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _lib.lib()
+        (idx,) = ctx.saved_tensors
+        B, C, H, W = ctx.shape
+        lay = _layout_of(dy)
+        if lay is None or lay[0] != _lib.NHWC or lay[1] != dy[0].numel():
+            dy = dy.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+        dx = torch.empty((B, H, W, C), dtype=dy.dtype, device=dy.device).permute(0, 3, 1, 2)
+        _lib.check(L.mrla_maxpool3x3s2_backward(_ptr(dy), _ptr(idx), _ptr(dx), B, C, H, W, _DTYPES[dy.dtype], _stream()),
+                   "mrla_maxpool3x3s2_backward")
+        launch_counter["bwd"] += L.mrla_last_launch_count()
+        return dx
+
+
+def max_pool(x: torch.Tensor, pool: "torch.nn.MaxPool2d") -> torch.Tensor:
+    """The stem's nn.MaxPool2d(3, 2, 1) on the NHWC kernels (byte tap index, gather backward); any other pooling
+    configuration or activation layout goes through the module itself — it is backbone, not the MRLA path."""
+    def _pair(v):
+        return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+    if (_pair(pool.kernel_size) == (3, 3) and _pair(pool.stride) == (2, 2) and _pair(pool.padding) == (1, 1)
+            and _pair(pool.dilation) == (1, 1) and not pool.ceil_mode and not pool.return_indices
+            and _max_pool_eligible(x)):
+        return _MaxPool3x3s2.apply(x)
+    return pool(x)

@@ -16,7 +16,7 @@ import torch.nn.functional as F
 from . import _lib
 from .drop import DropPath
 from .modules.mrla_light_module import mrla_light_layer
-from .ops import bn_act, light_tail
+from .ops import bn_act, light_tail, max_pool
 
 __all__ = ["ResNet_mrlal", "MRLA_Bottleneck", "mrla_module", "mrla_light_block_tail",
            "resnet50_mrlal", "resnet101_mrlal"]
@@ -172,7 +172,7 @@ class ResNet_mrlal(nn.Module):
         return nn.Sequential(*seq)
 
     def forward_features(self, x):
-        x = self.maxpool(bn_act(self.conv1(x), self.bn1, relu=True))
+        x = max_pool(bn_act(self.conv1(x), self.bn1, relu=True), self.maxpool)
         return self.layer4(self.layer3(self.layer2(self.layer1(x))))
 
     def forward(self, x):
