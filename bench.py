@@ -154,7 +154,7 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------ product arm
-def measure_tail_group(B, C, HW, dev, iters=10):
+def measure_tail_group(B, C, HW, dev, iters=10, bn3=True):
     """Device time (ms) of the folded MRLA-light tail op, forward and backward kernel groups, at one stage shape."""
     from mrla_b200 import _lib
     from mrla_b200.ops import LightCfg, light_tail
@@ -168,9 +168,11 @@ def measure_tail_group(B, C, HW, dev, iters=10):
          torch.ones(C, device=dev).requires_grad_(), torch.zeros(C, device=dev).requires_grad_()]
     rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
     cfg = LightCfg(dim_perhead=32, k_size=k, bn_mode=_lib.BN_TRAIN, residual=True, fuse_add_relu=True)
+    # the model hands the op the raw conv3 output plus the bn3 coefficients (sweep-1 MODE 6): time that variant
+    zc = torch.stack([torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev) * 0.1]).contiguous() if bn3 else None
 
     def fwd():
-        return light_tail(z, idt, *P, rm, rv, None, cfg=cfg)
+        return light_tail(z, idt, *P, rm, rv, None, cfg=cfg, z_coef=zc)
 
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
@@ -425,8 +427,9 @@ def run_product_arm(args):
                 traffic = None
         roof = {"bound": "hbm", "achieved": round(d["gbs"], 1), "peak": peak, "unit": "GB/s",
                 "frac": round(d["gbs"] / peak, 4), "traffic": traffic,
-                "kernel": "MRLA-light block tail fwd+bwd kernel group with the bottleneck's residual add+ReLU folded in, "
-                          "stage-1 shape (B,256,56,56) bf16 NHWC (add_relu+sweep1+mid+sweep2 / sweepA+mid+sweepB+finish); "
+                "kernel": "MRLA-light block tail fwd+bwd kernel group with the bottleneck's bn3 affine and residual "
+                          "add+ReLU folded in, stage-1 shape (B,256,56,56) bf16 NHWC (sweep 1 = bn3 affine + add + ReLU + "
+                          "moments, cluster mid kernel, sweep 2 / sweep A, cluster mid + gate kernels, sweep B, finish); "
                           "algorithmic bytes 9*N*2 per block (fwd R z,id W x,y; bwd R dy,x,id W dz,d_id)",
                 "peak_kind": peak_kind,
                 "launch_ms": {"fwd": round(d["fwd_ms"], 4), "bwd": round(d["bwd_ms"], 4)},

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define MRLA_ABI_VERSION 2
+#define MRLA_ABI_VERSION 3
 
 enum { MRLA_F32 = 0, MRLA_BF16 = 1, MRLA_F16 = 2 };
 enum { MRLA_NCHW = 0, MRLA_NHWC = 1 };
@@ -115,6 +115,9 @@ typedef struct MrlaLightArgs {
   const void* z;   /* if non-NULL: pre-activation; forward first forms x = relu(z + o) (resnet_mrla_light.py:113-114)
                       and WRITES it to the buffer `x` points to (which the caller keeps for backward)            */
   int64_t bs_z;    /* batch stride of z (elements)                                                               */
+  const float* z_coef; /* optional [2,C] (a_c, b_c): z is the RAW conv3 output and the bottleneck's bn3 apply
+                      (resnet_mrla_light.py:101-102) is folded in front of the add: z' = round_dtype(a_c*z + b_c),
+                      x = relu(z' + o).  Only where mrla_light_fwd_folds_bn() says so; NULL otherwise   */
 } MrlaLightArgs;
 
 int mrla_abi_version(void);
@@ -131,6 +134,10 @@ size_t mrla_light_bwd_scratch_bytes(const MrlaLightArgs* a);
 /* 1 if mrla_light_backward honours `fuse_relu_bwd` for these arguments (layout / shape / alignment), else 0
  * (the caller then applies the ReLU mask and the identity-gradient sum itself). */
 int mrla_light_bwd_fuses_relu(const MrlaLightArgs* a);
+
+/* 1 if mrla_light_forward folds a per-channel affine on z (`z_coef`) for these arguments (TMA sweep-1 path:
+ * NHWC, train-mode BN, o present, no GELU, aligned pointers), else 0 (the caller then applies bn3 itself). */
+int mrla_light_fwd_folds_bn(const MrlaLightArgs* a);
 
 /* y = residual*x + m_b*( BN( gate(x)*act(dwconv3x3(x)) + lambda*o ) ), plus saved statistics. */
 int mrla_light_forward(const MrlaLightArgs* a, void* stream);
@@ -215,7 +222,8 @@ typedef struct MrlaBnArgs {
   int32_t relu;            /* 1: y = relu(bn(x))                                                  */
   int32_t training;        /* 1: batch statistics; 0: running statistics                          */
   int32_t update_running;  /* 1: update running_mean / running_var in place (training only)       */
-  int32_t reserved0;
+  int32_t stats_only;      /* forward: compute stats / coef / running statistics but do not write y (the consumer
+                              applies a_c*x + b_c itself: MrlaLightArgs.z_coef)                                   */
   float eps, momentum;
   const void* x;           /* [M,C]                                                               */
   void* y;                 /* [M,C] (forward)                                                     */

@@ -11,7 +11,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmrla_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 F32, BF16, F16 = 0, 1, 2
 NCHW, NHWC = 0, 1
@@ -39,7 +39,7 @@ class MrlaLightArgs(ctypes.Structure):
         + [(n, _vp) for n in ("x", "o", "y", "wq", "wk", "wv", "lam", "gamma", "beta", "running_mean", "running_var",
                               "drop_scale", "mom", "gate", "mean", "rstd", "coef", "dy", "dx", "dout", "dwq", "dwk",
                               "dwv", "dlam", "dgamma", "dbeta", "gmom", "bcoef", "scratch")]
-        + [("scratch_bytes", ctypes.c_size_t), ("z", _vp), ("bs_z", _i64)]
+        + [("scratch_bytes", ctypes.c_size_t), ("z", _vp), ("bs_z", _i64), ("z_coef", _vp)]
     )
 
 
@@ -61,7 +61,7 @@ class MrlaBnArgs(ctypes.Structure):
     """Mirror of `struct MrlaBnArgs` (include/mrla_b200.h)."""
     _fields_ = (
         [("M", _i64)]
-        + [(n, _i32) for n in ("C", "dtype", "relu", "training", "update_running", "reserved0")]
+        + [(n, _i32) for n in ("C", "dtype", "relu", "training", "update_running", "stats_only")]
         + [("eps", _f32), ("momentum", _f32)]
         + [(n, _vp) for n in ("x", "y", "gamma", "beta", "running_mean", "running_var", "stats", "coef", "dy", "dx",
                               "dgamma", "dbeta", "scratch")]
@@ -74,7 +74,7 @@ _lock = threading.Lock()
 
 EXPORTS = (
     "mrla_abi_version", "mrla_build_info", "mrla_last_launch_count", "mrla_sizeof_light_args",
-    "mrla_light_bwd_scratch_bytes", "mrla_light_bwd_fuses_relu", "mrla_light_forward", "mrla_light_backward",
+    "mrla_light_bwd_scratch_bytes", "mrla_light_bwd_fuses_relu", "mrla_light_fwd_folds_bn", "mrla_light_forward", "mrla_light_backward",
     "mrla_nchw_to_nhwc", "mrla_add_relu", "mrla_sizeof_base_args", "mrla_base_bwd_scratch_bytes", "mrla_base_forward", "mrla_base_backward",
     "mrla_maxpool3x3s2_forward", "mrla_maxpool3x3s2_backward",
 )
@@ -107,6 +107,8 @@ def lib() -> ctypes.CDLL:
                                         ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]
         L.mrla_light_bwd_fuses_relu.restype = ctypes.c_int
         L.mrla_light_bwd_fuses_relu.argtypes = [ctypes.POINTER(MrlaLightArgs)]
+        L.mrla_light_fwd_folds_bn.restype = ctypes.c_int
+        L.mrla_light_fwd_folds_bn.argtypes = [ctypes.POINTER(MrlaLightArgs)]
         L.mrla_add_relu.restype = ctypes.c_int
         L.mrla_add_relu.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                                     ctypes.c_void_p]

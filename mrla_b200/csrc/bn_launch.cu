@@ -34,6 +34,7 @@ static int bn_forward_t(const MrlaBnArgs& a, const BnShape& s, cudaStream_t st) 
                                                  a.running_var, a.stats, a.coef, a.eps, a.momentum, a.training,
                                                  a.update_running);
   MRLA_CHECK_LAUNCH();
+  if (a.stats_only) return MRLA_OK;   // the consumer applies a_c x + b_c itself (MrlaLightArgs.z_coef)
   if (a.relu) k_bn_apply<T, true><<<s.nparts, 256, 0, st>>>(x, y, a.coef, s);
   else k_bn_apply<T, false><<<s.nparts, 256, 0, st>>>(x, y, a.coef, s);
   MRLA_CHECK_LAUNCH();
@@ -77,9 +78,10 @@ int mrla_bn_forward(const MrlaBnArgs* a, void* stream) {
   BnShape s;
   int rc = bn_plan(a, &s);
   if (rc) return rc;
-  if (!a->x || !a->y || !a->stats || !a->coef || !a->scratch) return MRLA_ERR_NULL;
+  if (!a->x || (!a->y && !a->stats_only) || !a->stats || !a->coef || !a->scratch) return MRLA_ERR_NULL;
+  if (a->stats_only && a->relu) return MRLA_ERR_UNSUPPORTED;
   if (!a->training && (!a->running_mean || !a->running_var)) return MRLA_ERR_NULL;
-  if (((uintptr_t)a->x % 16) || ((uintptr_t)a->y % 16)) return MRLA_ERR_ALIGN;
+  if (((uintptr_t)a->x % 16) || (a->y && ((uintptr_t)a->y % 16))) return MRLA_ERR_ALIGN;
   if (a->scratch_bytes < mrla_bn_scratch_bytes(a)) return MRLA_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (a->dtype) {

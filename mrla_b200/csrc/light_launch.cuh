@@ -131,7 +131,7 @@ int launch_tma_sweep(const MrlaLightArgs& a, cudaStream_t st, const TmaPlan& p, 
   CUtensorMap tx, to, tdy;
   if (make_nhwc_tmap(&tx, xptr, a.dtype, a.B, a.C, a.H, a.W, bs_x, p.CB, p.NQ * kCols + 2, p.G)) return MRLA_ERR_UNSUPPORTED;
   if (MODE == 3) to = tx;
-  else if (make_nhwc_tmap(&to, optr, a.dtype, a.B, a.C, a.H, a.W, bs_o, p.CB, p.NQ * kCols + (MODE == 5 ? 2 : 0), p.G))
+  else if (make_nhwc_tmap(&to, optr, a.dtype, a.B, a.C, a.H, a.W, bs_o, p.CB, p.NQ * kCols + ((MODE == 5 || MODE == 6) ? 2 : 0), p.G))
     return MRLA_ERR_UNSUPPORTED;
   tdy = to;
   if ((MODE == 2 || MODE == 4) && make_nhwc_tmap(&tdy, dyptr, a.dtype, a.B, a.C, a.H, a.W, bs_dy, p.CB, p.NQ * kCols, p.G))
@@ -143,6 +143,7 @@ int launch_tma_sweep(const MrlaLightArgs& a, cudaStream_t st, const TmaPlan& p, 
   P.x_bytes = p.x_bytes; P.o_bytes = p.o_bytes; P.stage_bytes = p.stage_bytes;
   P.wv = a.wv; P.mom = mom; P.coef = a.coef; P.y = a.y; P.bs_y = a.bs_y; P.res = a.residual ? 1.f : 0.f;
   P.wv_part = (MODE == 4) ? mom : nullptr;   // MODE 4 passes the partial buffer through `mom`
+  P.zcoef = (MODE == 6) ? a.z_coef : nullptr;
   const int threads = 32 + p.cons_threads;
 #define MRLA_TMA_LAUNCH1(CBV, BIGV)                                                                       \
   {                                                                                                       \
@@ -366,6 +367,17 @@ inline bool light_bwd_can_fuse_relu(const MrlaLightArgs& a) {
          make_tma_ring_plan(a, &tpr);
 }
 
+// does the forward of these arguments run the sweep-1 variant that folds the bn3 affine on z (MODE 6)?
+inline bool light_fwd_can_fold_bn(const MrlaLightArgs& a) {
+  if (a.layout != MRLA_NHWC || a.o == nullptr || a.z == nullptr || a.act != MRLA_ACT_NONE || a.bn_mode != MRLA_BN_TRAIN)
+    return false;
+  const int es = a.dtype == MRLA_F32 ? 4 : 2;
+  TmaPlan tp1, tp2, tp5;
+  return tma_ptr_ok(a.x, a.bs_x, es) && tma_ptr_ok(a.o, a.bs_o, es) && tma_ptr_ok(a.z, a.bs_z, es) &&
+         (a.bs_y * es) % 4 == 0 && make_tma_plan(a, 1, 6, &tp1) && make_tma_plan(a, 1, 0, &tp2) &&
+         make_tma_plan(a, 1, 6, &tp5, true);
+}
+
 // ------------------------------------------------------------------------------------ forward
 template <typename T, int LAYOUT, int CV, int ACT, bool HAS_O>
 int light_forward_impl(const MrlaLightArgs& a, cudaStream_t st) {
@@ -390,10 +402,12 @@ int light_forward_impl(const MrlaLightArgs& a, cudaStream_t st) {
     MrlaLightArgs a5 = a;
     a5.y = const_cast<void*>(a.x);
     a5.bs_y = a.bs_x;
-    rc = launch_tma_sweep<T, 0, 5>(a5, st, tp5, a.z, a.bs_z, a.o, a.bs_o, nullptr, 0, a.mom);
+    rc = a.z_coef ? launch_tma_sweep<T, 0, 6>(a5, st, tp5, a.z, a.bs_z, a.o, a.bs_o, nullptr, 0, a.mom)
+                  : launch_tma_sweep<T, 0, 5>(a5, st, tp5, a.z, a.bs_z, a.o, a.bs_o, nullptr, 0, a.mom);
     if (rc) return rc;
     x_ready = true;
   } else {
+    if (a.z_coef) return MRLA_ERR_UNSUPPORTED;   // callers ask mrla_light_fwd_folds_bn() first
     if (!x_ready) {
       const int64_t n = (int64_t)a.C * a.H * a.W;
       const int64_t v = 16 / es;

@@ -32,6 +32,7 @@ struct TmaSweepParams {
   int64_t bs_y;
   float res;
   float* wv_part;       // MODE 4: [grid/ncb, C, 9] per-CTA dWv partials
+  const float* zcoef;   // MODE 6: [2,C] affine applied to z in front of the fold (the bottleneck's bn3 apply)
 };
 
 // ---------------------------------------------------------------------------- packed helpers
@@ -192,14 +193,18 @@ __device__ __forceinline__ void conv9x4(const float2 (&top)[kWin], const float2 
 // MODE 0: forward moments (Σx ΣV ΣV² [ΣVo Σo Σo²]) ; MODE 1: forward apply (y) ; MODE 2: backward moments (Σdy ΣdyV [Σdyo])
 // MODE 3: MRLA-base F0 — y = dwconv3x3(x) stored into the V-cache slot, plus Σx (no o tile)
 // MODE 4: MRLA-base B4 — window tile = dV_t: dX and dWv ; MODE 5: MODE 0 with x = relu(z + o) formed (and stored) here
+// MODE 6: MODE 5 with z' = round(a_c z + b_c) first — z is the raw conv3 output and (a, b) the bn3 coefficients, so the
+//         bottleneck's bn3 apply pass (resnet_mrla_light.py:101-102) disappears as well
 // BIG: one 480-thread CTA per SM (W = 56 / 28); !BIG: <= 288 threads, two CTAs per SM (small images)
 template <typename T, int CB, int ACT, bool HAS_O, int MODE, bool BIG>
 __global__ void __launch_bounds__(BIG ? 480 : 288, BIG ? 1 : 2)
 k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_o,
                  const __grid_constant__ CUtensorMap tm_dy, TmaSweepParams P) {
   constexpr int NP = CB / 2;                                  // channel pairs per block
-  constexpr int NACC = (MODE == 0 || MODE == 5) ? (HAS_O ? 6 : 3) : (MODE == 2 ? (HAS_O ? 3 : 2) : (MODE == 3 ? 1 : 0));
-  constexpr bool XFOLD = (MODE == 5);   // x = relu(z + o) is formed here: the o tile carries halo columns too
+  constexpr bool MOM = (MODE == 0 || MODE == 5 || MODE == 6);   // forward moments
+  constexpr int NACC = MOM ? (HAS_O ? 6 : 3) : (MODE == 2 ? (HAS_O ? 3 : 2) : (MODE == 3 ? 1 : 0));
+  constexpr bool XFOLD = (MODE == 5 || MODE == 6);   // x = relu(z + o) is formed here: the o tile carries halo columns too
+  constexpr bool ZAFF = (MODE == 6);
   constexpr bool HAS_DY = (MODE == 2 || MODE == 4);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
@@ -271,6 +276,13 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   uint32_t oa = stages_s + P.x_bytes + tbase;     // address of o row r
   int cur_cb = -1;   // the grid is a multiple of ncb, so a CTA keeps its channel block: weights are loaded once
   float2 w9[9];
+  float2 za = f2(0.f, 0.f), zb = f2(0.f, 0.f);   // MODE 6: bn3 coefficients of this thread's channel pair
+  // MODE 6: window columns outside the image must stay exactly 0 (conv zero padding): the affine would turn the
+  // TMA zero fill into b_c
+  bool wvalid[kWin];
+#pragma unroll
+  for (int j = 0; j < kWin; ++j) wvalid[j] = (q * kCols - 1 + j) >= 0 && (q * kCols - 1 + j) < P.W;
+  const bool wedge = (q == 0) || (q * kCols + kCols >= P.W);   // this thread's window touches columns outside the image
   float2 dwf[MODE == 4 ? 9 : 1];   // MODE 4: dWv accumulators (flipped tap order), kept across all items of the CTA
 #pragma unroll
   for (int i = 0; i < (MODE == 4 ? 9 : 1); ++i) dwf[i] = f2(0.f, 0.f);
@@ -288,6 +300,10 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const int wi = (MODE == 4) ? 8 - i : i;   // MODE 4 correlates with the flipped kernel (transposed conv)
         w9[i] = chan_ok ? f2(P.wv[(int64_t)c * 9 + wi], P.wv[(int64_t)(c + 1) * 9 + wi]) : f2(0.f, 0.f);
       }
+      if (ZAFF && chan_ok) {
+        za = *reinterpret_cast<const float2*>(P.zcoef + c);
+        zb = *reinterpret_cast<const float2*>(P.zcoef + P.C + c);
+      }
     }
     float2 cA = f2(0.f, 0.f), cL = f2(0.f, 0.f), cD = f2(0.f, 0.f);
     if (MODE == 1 && chan_ok) {
@@ -304,7 +320,7 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     for (int i = 0; i < (NACC > 0 ? NACC : 1); ++i) { acc[i] = f2(0.f, 0.f); accb[i] = f2(0.f, 0.f); }
     // running pointer to this thread's first output column of the row being produced
     // MODE 5 writes x (row r, at fetch time); the others write the output row r-1
-    T* yrow = (MODE == 1 || MODE == 3 || MODE == 4 || MODE == 5) ? static_cast<T*>(P.y) + (int64_t)b * P.bs_y + (int64_t)(q * kCols) * P.C + c : nullptr;
+    T* yrow = (MODE == 1 || MODE == 3 || MODE == 4 || XFOLD) ? static_cast<T*>(P.y) + (int64_t)b * P.bs_y + (int64_t)(q * kCols) * P.C + c : nullptr;
     const int64_t y_row_stride = (int64_t)P.W * P.C;
     bool sv[kCols];
 #pragma unroll
@@ -333,11 +349,17 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
               // sees exactly the x that is stored — and written out for the own columns
 #pragma unroll
               for (int j = 0; j < kWin; ++j) {
-                const typename RawPair<T>::type xr =
-                    raw_relu<T>(raw_add<T>(lds_raw<T>(xa + j * CS), lds_raw<T>(oa + j * CS)));
+                typename RawPair<T>::type zr = lds_raw<T>(xa + j * CS);
+                if (ZAFF) zr = pack_pair<T>(ffma2(za, unpack_pair<T>(zr), zb));   // bn3 output in storage precision
+                const typename RawPair<T>::type xr = raw_relu<T>(raw_add<T>(zr, lds_raw<T>(oa + j * CS)));
                 win[i][j] = unpack_pair<T>(xr);
                 if (j >= 1 && j <= kCols)
                   if (sv[j - 1]) stg_raw<T>(yrow + (j - 1) * P.C, xr);
+              }
+              if (ZAFF && wedge) {   // warp-uniform: only the first / last column group of a row has such columns
+#pragma unroll
+                for (int j = 0; j < kWin; ++j)
+                  if (!wvalid[j]) win[i][j] = f2(0.f, 0.f);
               }
               yrow += y_row_stride;
             } else {
@@ -374,7 +396,7 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
               if (HAS_DY) gv = lds_pair<T>(ob + (HAS_O ? P.o_bytes : 0) + j * CS);
               const float2 xc = mid[j + 1];
               float2(&A)[NACC > 0 ? NACC : 1] = (j & 1) ? accb : acc;
-              if (MODE == 0 || MODE == 5) {
+              if (MOM) {
                 if (ragged && !cvalid[j]) v = f2(0.f, 0.f);
                 A[0] = fadd2(A[0], xc);
                 A[1] = fadd2(A[1], v);

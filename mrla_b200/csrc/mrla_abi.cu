@@ -99,6 +99,11 @@ int mrla_light_bwd_fuses_relu(const MrlaLightArgs* a) {
   return light_bwd_can_fuse_relu(*a) ? 1 : 0;
 }
 
+int mrla_light_fwd_folds_bn(const MrlaLightArgs* a) {
+  if (a == nullptr) return 0;
+  return light_fwd_can_fold_bn(*a) ? 1 : 0;
+}
+
 int mrla_light_forward(const MrlaLightArgs* a, void* stream) {
   g_launch_count = 0;
   int rc = check_common(a, false);

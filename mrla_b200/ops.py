@@ -172,7 +172,11 @@ def _want_nhwc(x: torch.Tensor) -> bool:
 # --------------------------------------------------------------------------------- the fused op
 class _LightTail(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, o, wq, wk, wv, lam, gamma, beta, running_mean, running_var, drop_scale, cfg: LightCfg, out):
+    def forward(ctx, x, o, wq, wk, wv, lam, gamma, beta, running_mean, running_var, drop_scale, cfg: LightCfg, out,
+                z_coef=None, z_coef_fn=None):
+        # z_coef / z_coef_fn are only used by _Bn3LightTail (which calls this method with its own context object):
+        # z_coef_fn(folds) is called once the library has said whether it folds the bn3 affine on z, and returns the
+        # [2,C] coefficients (folds) or None after applying bn3 itself into `x`'s storage
         _require_cuda(x, "x")
         L = _lib.lib()
         x_c, layout, bs_x = _canon(x)
@@ -240,6 +244,12 @@ class _LightTail(torch.autograd.Function):
         a.mom, a.gate, a.mean, a.rstd, a.coef = _ptr(mom), _ptr(gate), _ptr(stats[0]), _ptr(stats[1]), _ptr(coef)
         if z_c is not None:
             a.z, a.bs_z = _ptr(z_c), C * H * W
+        if z_coef_fn is not None:
+            folds = z_c is not None and bool(L.mrla_light_fwd_folds_bn(ctypes.byref(a)))
+            z_coef = z_coef_fn(folds, z_c if z_c is not None else x_c)
+            ctx.bn3_folded = z_coef is not None
+        if z_coef is not None:
+            a.z_coef = _ptr(z_coef)
         _lib.check(L.mrla_light_forward(ctypes.byref(a), _stream()), "mrla_light_forward")
         _Prof.end("light_fwd", (B, C, H, W, x.dtype, layout, bool(cfg.fuse_add_relu)), ev)
         launch_counter["fwd"] += L.mrla_last_launch_count()
@@ -323,15 +333,154 @@ class _LightTail(torch.autograd.Function):
                  back(0, dwqk[0]), back(1, dwqk[1]), back(2, dwv),
                  back(3, dch[0]) if ctx.has_o else None,
                  back(4, dch[1]) if has_bn else None, back(5, dch[2]) if has_bn else None,
-                 None, None, None, None, None)
+                 None, None, None, None, None, None, None)
         return grads
 
 
+class _Ctx:
+    """Stand-in for an autograd context so that one Function can run another's forward / backward inside its own."""
+
+    def __init__(self, saved=()):
+        self.saved_tensors = tuple(saved)
+
+    def save_for_backward(self, *tensors):
+        self.saved_tensors = tuple(tensors)
+
+    def mark_dirty(self, *tensors):
+        pass
+
+
+class _Bn3LightTail(torch.autograd.Function):
+    """bn3 + residual add + ReLU + MRLA-light tail of one bottleneck as ONE autograd node:
+    `c3` is the raw conv3 output.  Forward: BatchNorm statistics of c3 (mrla_bn_forward, stats_only) -> sweep 1 applies
+    a_c*c3 + b_c, adds the identity, ReLUs, stores x and takes the moments (MODE 6) -> mid -> sweep 2.  Backward: the
+    tail's backward leaves dz (= gradient of the bn3 output) and the total identity gradient, then mrla_bn_backward turns
+    dz into d(c3), d(gamma3), d(beta3).  Replaces resnet_mrla_light.py:101-102 + :113-116.  Only for tails the library
+    folds (bn3_tail_eligible); every other case keeps bn3 as its own op (ops.bn_act) in front of light_tail."""
+
+    @staticmethod
+    def forward(ctx, c3, o, w3, b3, rm3, rv3, bn3_args, wq, wk, wv, lam, gamma, beta, running_mean, running_var,
+                drop_scale, cfg: LightCfg):
+        L = _lib.lib()
+        training3, update3, momentum3, eps3 = bn3_args
+        B, C, H, W = c3.shape
+        f32 = dict(dtype=torch.float32, device=c3.device)
+        stats3 = torch.empty((2, C), **f32)
+        coef3 = torch.empty((2, C), **f32)
+        w3_32, b3_32 = _f32(w3), _f32(b3)
+        keep = {}
+
+        def bn3(folds, src):
+            # src: the dense NHWC buffer holding c3; statistics only — sweep 1 applies the affine
+            if not folds:
+                raise RuntimeError("mrla_b200: bn3 fold requested for a tail the library does not fold "
+                                   "(callers check bn3_tail_eligible first)")
+            a = _lib.MrlaBnArgs()
+            a.M, a.C, a.dtype = B * H * W, C, _DTYPES[src.dtype]
+            a.relu, a.training, a.update_running = 0, int(training3), int(update3)
+            a.stats_only = int(folds)
+            a.eps, a.momentum = eps3, momentum3
+            a.x, a.gamma, a.beta = _ptr(src), _ptr(w3_32), _ptr(b3_32)
+            a.running_mean, a.running_var = _ptr(rm3), _ptr(rv3)
+            a.stats, a.coef = _ptr(stats3), _ptr(coef3)
+            nbytes = L.mrla_bn_scratch_bytes(ctypes.byref(a))
+            scratch = torch.empty((max(nbytes, 4) + 3) // 4, **f32)
+            a.scratch, a.scratch_bytes = _ptr(scratch), scratch.numel() * 4
+            _lib.check(L.mrla_bn_forward(ctypes.byref(a), _stream()), "mrla_bn_forward")
+            launch_counter["fwd"] += L.mrla_last_launch_count()
+            keep["src"] = src
+            return coef3
+
+        inner = _Ctx()
+        y = _LightTail.forward(inner, c3, o, wq, wk, wv, lam, gamma, beta, running_mean, running_var, drop_scale, cfg,
+                               None, None, bn3)
+        ctx.inner = {k: v for k, v in inner.__dict__.items() if k != "saved_tensors"}
+        ctx.n_inner = len(inner.saved_tensors)
+        ctx.bn3_meta = (bool(training3), eps3, momentum3)
+        ctx.bn3_param_meta = [(p.shape, p.dtype, p.stride()) if p is not None else None for p in (w3, b3)]
+        ctx.save_for_backward(*inner.saved_tensors, keep["src"], w3_32, stats3, coef3)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _lib.lib()
+        saved = ctx.saved_tensors
+        inner = _Ctx(saved[:ctx.n_inner])
+        inner.__dict__.update(ctx.inner)
+        g = _LightTail.backward(inner, dy)
+        dz, d_id = g[0], g[1]
+        c3, w3_32, stats3, coef3 = saved[ctx.n_inner:]
+        training3, eps3, momentum3 = ctx.bn3_meta
+        B, C, H, W = c3.shape
+        f32 = dict(dtype=torch.float32, device=c3.device)
+        dc3 = _empty_like_layout(c3, _lib.NHWC)
+        dgb = torch.empty((2, C), **f32)
+        a = _lib.MrlaBnArgs()
+        a.M, a.C, a.dtype = B * H * W, C, _DTYPES[c3.dtype]
+        a.relu, a.training = 0, int(training3)
+        a.eps, a.momentum = eps3, momentum3
+        a.x, a.gamma, a.stats, a.coef = _ptr(c3), _ptr(w3_32), _ptr(stats3), _ptr(coef3)
+        a.dy, a.dx, a.dgamma, a.dbeta = _ptr(dz), _ptr(dc3), _ptr(dgb[0]), _ptr(dgb[1])
+        nbytes = L.mrla_bn_scratch_bytes(ctypes.byref(a))
+        scratch = torch.empty((max(nbytes, 4) + 3) // 4, **f32)
+        a.scratch, a.scratch_bytes = _ptr(scratch), scratch.numel() * 4
+        _lib.check(L.mrla_bn_backward(ctypes.byref(a), _stream()), "mrla_bn_backward")
+        launch_counter["bwd"] += L.mrla_last_launch_count()
+        dw3 = _like_param(dgb[0], ctx.bn3_param_meta[0]) if ctx.bn3_param_meta[0] is not None else None
+        db3 = _like_param(dgb[1], ctx.bn3_param_meta[1]) if ctx.bn3_param_meta[1] is not None else None
+        return (dc3, d_id, dw3, db3, None, None, None) + tuple(g[2:8]) + (None, None, None, None)
+
+
+def bn3_tail_eligible(c3: torch.Tensor, o: torch.Tensor, bn3: "torch.nn.BatchNorm2d", cfg: LightCfg) -> bool:
+    """Can bn3 be folded into the tail op for these tensors?  (Asks the library's own planner through
+    mrla_light_fwd_folds_bn with the layout / strides / alignment the op would use.)"""
+    if not (cfg.fuse_add_relu and cfg.bn_mode == _lib.BN_TRAIN and cfg.act == _lib.ACT_NONE):
+        return False
+    if not (bn3.training or bn3.running_mean is None) or bn3.weight is None or bn3.bias is None:
+        return False
+    if bn3.running_mean is not None and bn3.running_mean.dtype != torch.float32:
+        return False
+    if not bn_act_eligible(c3) or o is None or o.shape != c3.shape or o.dtype != c3.dtype or not o.is_cuda:
+        return False
+    lay_o = _layout_of(o)
+    B, C, H, W = c3.shape
+    n = C * H * W
+    if lay_o is None or lay_o[0] != _lib.NHWC or lay_o[1] != n or o.data_ptr() % 16:
+        return False
+    a = _lib.MrlaLightArgs()
+    a.B, a.C, a.H, a.W = B, C, H, W
+    a.dim_perhead, a.k_size = cfg.dim_perhead, cfg.k_size
+    a.dtype, a.layout, a.act, a.bn_mode = _DTYPES[c3.dtype], _lib.NHWC, cfg.act, cfg.bn_mode
+    a.bs_x = a.bs_o = a.bs_y = a.bs_z = n
+    a.x, a.o, a.z = _ptr(c3), _ptr(o), _ptr(c3)   # x / y buffers are fresh allocations with the same alignment
+    return bool(_lib.lib().mrla_light_fwd_folds_bn(ctypes.byref(a)))
+
+
+def bn3_light_tail(c3: torch.Tensor, o: torch.Tensor, bn3: "torch.nn.BatchNorm2d", wq, wk, wv, lam, gamma, beta,
+                   running_mean, running_var, drop_scale, *, cfg: LightCfg) -> torch.Tensor:
+    """`tail(bn3(c3), o)` with bn3's apply folded into sweep 1; callers check bn3_tail_eligible() first."""
+    update = bn3.training and bn3.track_running_stats and bn3.running_mean is not None
+    if update:
+        bn3.num_batches_tracked += 1
+        momentum = bn3.momentum if bn3.momentum is not None else 1.0 / float(int(bn3.num_batches_tracked))
+    else:
+        momentum = 0.0
+    return _Bn3LightTail.apply(c3, o, bn3.weight, bn3.bias, bn3.running_mean, bn3.running_var,
+                               (True, update, momentum, bn3.eps), wq, wk, wv, lam, gamma, beta, running_mean, running_var,
+                               drop_scale, cfg)
+
+
 def light_tail(x: torch.Tensor, o: Optional[torch.Tensor], wq, wk, wv, lam=None, gamma=None, beta=None,
-               running_mean=None, running_var=None, drop_scale=None, *, cfg: LightCfg, out=None) -> torch.Tensor:
+               running_mean=None, running_var=None, drop_scale=None, *, cfg: LightCfg, out=None,
+               z_coef: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Fused MRLA-light tail (see module docstring).  `x`/`o` are logical [B,C,H,W] tensors, either
-    NCHW-contiguous or channels-last (any batch stride); the result has the layout of `x`."""
-    return _LightTail.apply(x, o, wq, wk, wv, lam, gamma, beta, running_mean, running_var, drop_scale, cfg, out)
+    NCHW-contiguous or channels-last (any batch stride); the result has the layout of `x`.
+
+    `z_coef` ([2,C] fp32, with cfg.fuse_add_relu): constant per-channel affine applied to `x` (= z) in front of the add,
+    as bn3_light_tail does with the bn3 coefficients; no gradient flows to it (kernel-level benchmarks use it to time
+    the sweep-1 variant the model runs)."""
+    return _LightTail.apply(x, o, wq, wk, wv, lam, gamma, beta, running_mean, running_var, drop_scale, cfg, out,
+                            z_coef, None)
 
 
 # ===================================================================================== MRLA-base

@@ -16,7 +16,7 @@ import torch.nn.functional as F
 from . import _lib
 from .drop import DropPath
 from .modules.mrla_light_module import mrla_light_layer
-from .ops import bn_act, light_tail, max_pool
+from .ops import bn3_light_tail, bn3_tail_eligible, bn_act, light_tail, max_pool
 
 __all__ = ["ResNet_mrlal", "MRLA_Bottleneck", "mrla_module", "mrla_light_block_tail",
            "resnet50_mrlal", "resnet101_mrlal"]
@@ -43,14 +43,18 @@ def _bn_effective_momentum(bn: nn.BatchNorm2d) -> float:
 
 
 def mrla_light_block_tail(out, identity, mrla: mrla_module, bn: nn.BatchNorm2d, drop_path: nn.Module,
-                          pre_add_relu: bool = False):
+                          pre_add_relu: bool = False, pre_bn: nn.BatchNorm2d = None):
     """Fused `out + drop_path(bn(mrla(out, identity)))` (reference :116; mmdet variant
     mmdetection/mmdet/models/backbones/resnet_mrlal.py:116 = eval-mode BN, no DropPath).
 
     `pre_add_relu=True`: `out` is the pre-activation bn3 output and the residual add + ReLU of the bottleneck
     (`out += identity; out = relu(out)`, reference :113-114) is folded into the op: one pass forms
     x = relu(out + identity), and the backward epilogue of sweep B emits d(out) = dx*[x>0] and the TOTAL
-    identity gradient directly (no threshold_backward / gradient-accumulation passes)."""
+    identity gradient directly (no threshold_backward / gradient-accumulation passes).
+
+    `pre_bn` (with pre_add_relu): `out` is the RAW conv3 output and `pre_bn` the bottleneck's bn3 (reference :101-102).
+    Where the library folds it, bn3 becomes statistics + a per-channel affine applied inside sweep 1 (one autograd node
+    for bn3 + add + ReLU + tail); otherwise bn3 runs as its own op first."""
     layer = mrla.mrla
     use_batch_stats = bn.training or bn.running_mean is None
     if use_batch_stats:
@@ -62,8 +66,14 @@ def mrla_light_block_tail(out, identity, mrla: mrla_module, bn: nn.BatchNorm2d, 
     scale = drop_path.scale(out) if isinstance(drop_path, DropPath) else None
     cfg = layer.cfg(bn_mode=mode, residual=True, update_running=update, eps=bn.eps, momentum=momentum,
                     fuse_add_relu=pre_add_relu)
-    y = light_tail(out, identity, layer.Wq.weight, layer.Wk.weight, layer.Wv.weight, mrla.lambda_t,
-                   bn.weight, bn.bias, bn.running_mean, bn.running_var, scale, cfg=cfg)
+    if pre_bn is not None and pre_add_relu and bn3_tail_eligible(out, identity, pre_bn, cfg):
+        y = bn3_light_tail(out, identity, pre_bn, layer.Wq.weight, layer.Wk.weight, layer.Wv.weight, mrla.lambda_t,
+                           bn.weight, bn.bias, bn.running_mean, bn.running_var, scale, cfg=cfg)
+    else:
+        if pre_bn is not None:
+            out = bn_act(out, pre_bn)
+        y = light_tail(out, identity, layer.Wq.weight, layer.Wk.weight, layer.Wv.weight, mrla.lambda_t,
+                       bn.weight, bn.bias, bn.running_mean, bn.running_var, scale, cfg=cfg)
     if update:
         bn.num_batches_tracked += 1
     return y
@@ -113,9 +123,9 @@ class MRLA_Bottleneck(nn.Module):
             identity = self.downsample(x)
         out = bn_act(self.conv1(x), self.bn1, relu=True)
         out = bn_act(self.conv2(out), self.bn2, relu=True)
-        out = bn_act(self.conv3(out), self.bn3)
-        # `out += identity; relu` (reference :113-114) is folded into the tail op
-        return mrla_light_block_tail(out, identity, self.mrla, self.bn_mrla, self.drop_path, pre_add_relu=True)
+        # bn3 and `out += identity; relu` (reference :101-102, :113-114) are folded into the tail op
+        return mrla_light_block_tail(self.conv3(out), identity, self.mrla, self.bn_mrla, self.drop_path,
+                                     pre_add_relu=True, pre_bn=self.bn3)
 
 
 class ResNet_mrlal(nn.Module):
