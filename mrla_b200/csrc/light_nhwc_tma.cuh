@@ -282,7 +282,6 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   bool wvalid[kWin];
 #pragma unroll
   for (int j = 0; j < kWin; ++j) wvalid[j] = (q * kCols - 1 + j) >= 0 && (q * kCols - 1 + j) < P.W;
-  const bool wedge = (q == 0) || (q * kCols + kCols >= P.W);   // this thread's window touches columns outside the image
   float2 dwf[MODE == 4 ? 9 : 1];   // MODE 4: dWv accumulators (flipped tap order), kept across all items of the CTA
 #pragma unroll
   for (int i = 0; i < (MODE == 4 ? 9 : 1); ++i) dwf[i] = f2(0.f, 0.f);
@@ -351,15 +350,11 @@ k_light_nhwc_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
               for (int j = 0; j < kWin; ++j) {
                 typename RawPair<T>::type zr = lds_raw<T>(xa + j * CS);
                 if (ZAFF) zr = pack_pair<T>(ffma2(za, unpack_pair<T>(zr), zb));   // bn3 output in storage precision
-                const typename RawPair<T>::type xr = raw_relu<T>(raw_add<T>(zr, lds_raw<T>(oa + j * CS)));
+                typename RawPair<T>::type xr = raw_relu<T>(raw_add<T>(zr, lds_raw<T>(oa + j * CS)));
+                if (ZAFF && !wvalid[j]) xr = pack_pair<T>(f2(0.f, 0.f));
                 win[i][j] = unpack_pair<T>(xr);
                 if (j >= 1 && j <= kCols)
                   if (sv[j - 1]) stg_raw<T>(yrow + (j - 1) * P.C, xr);
-              }
-              if (ZAFF && wedge) {   // warp-uniform: only the first / last column group of a row has such columns
-#pragma unroll
-                for (int j = 0; j < kWin; ++j)
-                  if (!wvalid[j]) win[i][j] = f2(0.f, 0.f);
               }
               yrow += y_row_stride;
             } else {
