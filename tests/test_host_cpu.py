@@ -107,3 +107,31 @@ def test_layout_classifier():
     assert _layout_of(x[:, :, ::2]) is None
     with pytest.raises(ValueError):
         tokens_as_image(torch.randn(2, 15, 8))
+
+
+def test_bn3_fold_and_pool_host_logic_on_cpu_tensors():
+    """The bn3 fold and the stem pooling are decided on the host: CPU tensors are never eligible, the pooling (backbone)
+    then runs the module itself, and the MRLA tail still refuses to run without the CUDA kernels."""
+    import torch.nn as nn
+    from mrla_b200 import _lib
+    from mrla_b200.ops import LightCfg, bn3_tail_eligible, max_pool
+    from mrla_b200.resnet_mrla_light import MRLA_Bottleneck
+    cfg = LightCfg(dim_perhead=32, k_size=3, bn_mode=_lib.BN_TRAIN, residual=True, fuse_add_relu=True)
+    c3 = torch.randn(2, 64, 7, 7).contiguous(memory_format=torch.channels_last)
+    assert not bn3_tail_eligible(c3, c3.clone(), nn.BatchNorm2d(64), cfg)
+    assert not bn3_tail_eligible(c3, c3.clone(), nn.BatchNorm2d(64), cfg._replace(fuse_add_relu=False))
+    pool = nn.MaxPool2d(3, 2, 1)
+    x = torch.randn(2, 8, 9, 9)
+    assert torch.equal(max_pool(x, pool), pool(x))
+    blk = MRLA_Bottleneck(64, 16).train()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        blk(torch.randn(2, 64, 7, 7))
+
+
+def test_light_args_mirror_has_the_producer_fold_fields():
+    """ABI v3: z / bs_z / z_coef close the struct, in the order of include/mrla_b200.h."""
+    from mrla_b200 import _lib
+    names = [f[0] for f in _lib.MrlaLightArgs._fields_]
+    assert names[-4:] == ["scratch_bytes", "z", "bs_z", "z_coef"]
+    assert _lib.ABI_VERSION == 3
+    assert [f[0] for f in _lib.MrlaBnArgs._fields_][6] == "stats_only"
