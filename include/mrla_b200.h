@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define MRLA_ABI_VERSION 3
+#define MRLA_ABI_VERSION 4
 
 enum { MRLA_F32 = 0, MRLA_BF16 = 1, MRLA_F16 = 2 };
 enum { MRLA_NCHW = 0, MRLA_NHWC = 1 };
@@ -74,7 +74,10 @@ typedef struct MrlaLightArgs {
                              (resnet_mrla_light.py:113-114).  Then `dx` receives dz = dx_total*[x>0] and
                              `dout` receives the TOTAL identity gradient lam*dS + dz, which replaces the
                              reference's threshold_backward and gradient-accumulation passes.          */
-  int32_t reserved0;
+  int32_t x_virtual;      /* 1: x = relu(z_coef.a*z + z_coef.b + o) is NEVER materialised (round 2): forward and backward
+                             re-form it from the raw conv3 output `z`, `z_coef` and `o` inside every sweep; `x` may be NULL.
+                             Needs z, z_coef, bn_mode TRAIN and (backward) fuse_relu_bwd = 1; only where
+                             mrla_light_virtual_x() says so.  Backward then also fills `dz_sums`.                        */
   float eps, momentum;  /* BatchNorm2d eps / momentum                                          */
   int64_t bs_x, bs_o, bs_y, bs_dy, bs_dx, bs_do; /* batch strides (elements)                    */
   /* ---- forward tensors ---- */
@@ -118,6 +121,9 @@ typedef struct MrlaLightArgs {
   const float* z_coef; /* optional [2,C] (a_c, b_c): z is the RAW conv3 output and the bottleneck's bn3 apply
                       (resnet_mrla_light.py:101-102) is folded in front of the add: z' = round_dtype(a_c*z + b_c),
                       x = relu(z' + o).  Only where mrla_light_fwd_folds_bn() says so; NULL otherwise   */
+  float* dz_sums;  /* backward with x_virtual: [2,C] sum_{b,h,w} dz and sum dz*z — the two reductions of bn3's backward
+                      (resnet_mrla_light.py:101-102), accumulated in the sweep-B epilogue so that mrla_bn_backward
+                      (MrlaBnArgs.sums) needs no reduction pass over dz and z.  NULL: not produced.                  */
 } MrlaLightArgs;
 
 int mrla_abi_version(void);
@@ -138,6 +144,10 @@ int mrla_light_bwd_fuses_relu(const MrlaLightArgs* a);
 /* 1 if mrla_light_forward folds a per-channel affine on z (`z_coef`) for these arguments (TMA sweep-1 path:
  * NHWC, train-mode BN, o present, no GELU, aligned pointers), else 0 (the caller then applies bn3 itself). */
 int mrla_light_fwd_folds_bn(const MrlaLightArgs* a);
+
+/* 1 if forward AND backward of these arguments (z, z_coef, o, shapes, alignment as they will be passed) run the sweeps
+ * that re-form x on the fly (`x_virtual`), else 0 (the caller then lets forward materialise x as before). */
+int mrla_light_virtual_x(const MrlaLightArgs* a);
 
 /* y = residual*x + m_b*( BN( gate(x)*act(dwconv3x3(x)) + lambda*o ) ), plus saved statistics. */
 int mrla_light_forward(const MrlaLightArgs* a, void* stream);
@@ -239,6 +249,8 @@ typedef struct MrlaBnArgs {
   float* dbeta;            /* [C] or NULL                                                         */
   float* scratch;          /* mrla_bn_scratch_bytes()                                             */
   size_t scratch_bytes;
+  const float* sums;       /* backward, optional: [2,C] precomputed sum dy, sum dy*x (MrlaLightArgs.dz_sums): the
+                              reduction pass over dy and x is skipped (relu must be 0)                            */
 } MrlaBnArgs;
 
 size_t mrla_sizeof_bn_args(void);

@@ -11,7 +11,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmrla_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 F32, BF16, F16 = 0, 1, 2
 NCHW, NHWC = 0, 1
@@ -33,13 +33,13 @@ class MrlaLightArgs(ctypes.Structure):
     """Mirror of `struct MrlaLightArgs` (include/mrla_b200.h) — field order must match."""
     _fields_ = (
         [(n, _i32) for n in ("B", "C", "H", "W", "dim_perhead", "k_size", "dtype", "layout", "act", "bn_mode",
-                             "residual", "update_running", "fuse_relu_bwd", "reserved0")]
+                             "residual", "update_running", "fuse_relu_bwd", "x_virtual")]
         + [("eps", _f32), ("momentum", _f32)]
         + [(n, _i64) for n in ("bs_x", "bs_o", "bs_y", "bs_dy", "bs_dx", "bs_do")]
         + [(n, _vp) for n in ("x", "o", "y", "wq", "wk", "wv", "lam", "gamma", "beta", "running_mean", "running_var",
                               "drop_scale", "mom", "gate", "mean", "rstd", "coef", "dy", "dx", "dout", "dwq", "dwk",
                               "dwv", "dlam", "dgamma", "dbeta", "gmom", "bcoef", "scratch")]
-        + [("scratch_bytes", ctypes.c_size_t), ("z", _vp), ("bs_z", _i64), ("z_coef", _vp)]
+        + [("scratch_bytes", ctypes.c_size_t), ("z", _vp), ("bs_z", _i64), ("z_coef", _vp), ("dz_sums", _vp)]
     )
 
 
@@ -65,7 +65,7 @@ class MrlaBnArgs(ctypes.Structure):
         + [("eps", _f32), ("momentum", _f32)]
         + [(n, _vp) for n in ("x", "y", "gamma", "beta", "running_mean", "running_var", "stats", "coef", "dy", "dx",
                               "dgamma", "dbeta", "scratch")]
-        + [("scratch_bytes", ctypes.c_size_t)]
+        + [("scratch_bytes", ctypes.c_size_t), ("sums", _vp)]
     )
 
 
@@ -74,7 +74,7 @@ _lock = threading.Lock()
 
 EXPORTS = (
     "mrla_abi_version", "mrla_build_info", "mrla_last_launch_count", "mrla_sizeof_light_args",
-    "mrla_light_bwd_scratch_bytes", "mrla_light_bwd_fuses_relu", "mrla_light_fwd_folds_bn", "mrla_light_forward", "mrla_light_backward",
+    "mrla_light_bwd_scratch_bytes", "mrla_light_bwd_fuses_relu", "mrla_light_fwd_folds_bn", "mrla_light_virtual_x", "mrla_light_forward", "mrla_light_backward",
     "mrla_nchw_to_nhwc", "mrla_add_relu", "mrla_sizeof_base_args", "mrla_base_bwd_scratch_bytes", "mrla_base_forward", "mrla_base_backward",
     "mrla_maxpool3x3s2_forward", "mrla_maxpool3x3s2_backward",
 )
@@ -109,6 +109,8 @@ def lib() -> ctypes.CDLL:
         L.mrla_light_bwd_fuses_relu.argtypes = [ctypes.POINTER(MrlaLightArgs)]
         L.mrla_light_fwd_folds_bn.restype = ctypes.c_int
         L.mrla_light_fwd_folds_bn.argtypes = [ctypes.POINTER(MrlaLightArgs)]
+        L.mrla_light_virtual_x.restype = ctypes.c_int
+        L.mrla_light_virtual_x.argtypes = [ctypes.POINTER(MrlaLightArgs)]
         L.mrla_add_relu.restype = ctypes.c_int
         L.mrla_add_relu.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                                     ctypes.c_void_p]

@@ -48,11 +48,14 @@ static int bn_backward_t(const MrlaBnArgs& a, const BnShape& s, cudaStream_t st)
   T* dx = static_cast<T*>(a.dx);
   float* bcoef = a.scratch + (size_t)s.nparts * 2 * a.C;
   const size_t sm = 256 * 2 * kSV * sizeof(float);
-  if (a.relu) k_bn_bwd_reduce<T, true><<<s.nparts, 256, sm, st>>>(dy, x, a.coef, a.scratch, s);
-  else k_bn_bwd_reduce<T, false><<<s.nparts, 256, sm, st>>>(dy, x, a.coef, a.scratch, s);
-  MRLA_CHECK_LAUNCH();
-  k_bn_bwd_finalize<<<(a.C + 31) / 32, 1024, 0, st>>>(a.scratch, s.nparts, a.C, (double)a.M, a.gamma, a.stats, bcoef,
-                                                     a.dgamma, a.dbeta, a.training);
+  if (a.sums == nullptr) {
+    if (a.relu) k_bn_bwd_reduce<T, true><<<s.nparts, 256, sm, st>>>(dy, x, a.coef, a.scratch, s);
+    else k_bn_bwd_reduce<T, false><<<s.nparts, 256, sm, st>>>(dy, x, a.coef, a.scratch, s);
+    MRLA_CHECK_LAUNCH();
+  }
+  // a.sums: the producer of dy (sweep B of the MRLA tail, MrlaLightArgs.dz_sums) already reduced sum dy, sum dy*x
+  k_bn_bwd_finalize<<<(a.C + 31) / 32, 1024, 0, st>>>(a.sums ? a.sums : a.scratch, a.sums ? 1 : s.nparts, a.C, (double)a.M,
+                                                     a.gamma, a.stats, bcoef, a.dgamma, a.dbeta, a.training);
   MRLA_CHECK_LAUNCH();
   if (a.relu) k_bn_bwd_apply<T, true><<<s.nparts, 256, 0, st>>>(dy, x, dx, a.coef, bcoef, s);
   else k_bn_bwd_apply<T, false><<<s.nparts, 256, 0, st>>>(dy, x, dx, a.coef, bcoef, s);
@@ -97,6 +100,7 @@ int mrla_bn_backward(const MrlaBnArgs* a, void* stream) {
   int rc = bn_plan(a, &s);
   if (rc) return rc;
   if (!a->x || !a->dy || !a->dx || !a->stats || !a->coef || !a->scratch) return MRLA_ERR_NULL;
+  if (a->sums && a->relu) return MRLA_ERR_UNSUPPORTED;
   if (((uintptr_t)a->x % 16) || ((uintptr_t)a->dy % 16) || ((uintptr_t)a->dx % 16)) return MRLA_ERR_ALIGN;
   if (a->scratch_bytes < mrla_bn_scratch_bytes(a)) return MRLA_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

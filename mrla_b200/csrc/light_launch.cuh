@@ -7,10 +7,26 @@
 #include "light_nhwc_tma.cuh"
 #include "light_nhwc_ring.cuh"
 #include "layout_kernels.cuh"
+#include "light_v7_launch.cuh"
 
 namespace mrla {
 
 extern thread_local int g_launch_count;
+
+// the v7 kernels are compiled in their own translation units (v7_<dtype>.cu)
+#define MRLA_V7_EXTERN(T)                                                                                                  \
+  extern template int v7_launch_fwd<T, 0>(const MrlaLightArgs&, cudaStream_t, const V7Plan&, bool, const void*, int64_t,  \
+                                          float*, int, int);                                                               \
+  extern template int v7_launch_fwd<T, 1>(const MrlaLightArgs&, cudaStream_t, const V7Plan&, bool, const void*, int64_t,  \
+                                          float*, int, int);                                                               \
+  extern template int v7_launch_fwd<T, 2>(const MrlaLightArgs&, cudaStream_t, const V7Plan&, bool, const void*, int64_t,  \
+                                          float*, int, int);                                                               \
+  extern template int v7_launch_bwd<T>(const MrlaLightArgs&, cudaStream_t, const V7Plan&, bool, bool, const void*, int64_t, \
+                                       float*, float*, float*);
+MRLA_V7_EXTERN(float)
+MRLA_V7_EXTERN(__nv_bfloat16)
+MRLA_V7_EXTERN(__half)
+#undef MRLA_V7_EXTERN
 
 struct LightPlan {
   int slots;      // slots per CTA
@@ -392,11 +408,26 @@ int light_forward_impl(const MrlaLightArgs& a, cudaStream_t st) {
   T* y = static_cast<T*>(a.y);
   const int es = a.dtype == MRLA_F32 ? 4 : 2;
   TmaPlan tp1, tp2, tp5;
-  const bool tma_ok = LAYOUT == MRLA_NHWC && HAS_O && tma_ptr_ok(a.x, a.bs_x, es) && tma_ptr_ok(a.o, a.bs_o, es) &&
+  // ---- v7 sweeps (light_v7.cuh): x re-formed on the fly (x_virtual) or a plain materialised x
+  V7Plan v1, v2;
+  const bool v7_base = LAYOUT == MRLA_NHWC && HAS_O && ACT == 0 && v7_ptr_ok(a.o, a.bs_o, es) && v7_ptr_ok(a.y, a.bs_y, es);
+  if (a.x_virtual) {
+    if (!(v7_base && full && a.z && a.z_coef && v7_ptr_ok(a.z, a.bs_z, es) && v7_plan(a, V7_S1, true, &v1) &&
+          v7_plan(a, V7_S2, true, &v2)))
+      return MRLA_ERR_UNSUPPORTED;   // callers ask mrla_light_virtual_x() first
+  }
+  const bool v7x = a.x_virtual != 0;
+  const bool v7p = !v7x && v7_base && a.z == nullptr && v7_ptr_ok(a.x, a.bs_x, es) && v7_plan(a, V7_S1, false, &v1) &&
+                   v7_plan(a, V7_S2, false, &v2);
+  const bool tma_ok = !v7x && LAYOUT == MRLA_NHWC && HAS_O && tma_ptr_ok(a.x, a.bs_x, es) && tma_ptr_ok(a.o, a.bs_o, es) &&
                       (a.bs_y * es) % 4 == 0 && make_tma_plan(a, 1, 6, &tp1) && make_tma_plan(a, 1, 0, &tp2);
   // optional producer fold: x = relu(z + o)
-  bool x_ready = (a.z == nullptr);
+  bool x_ready = (a.z == nullptr) || v7x;
   if (!x_ready && !HAS_O) return MRLA_ERR_NULL;
+  if (v7x) {
+    rc = v7_launch_fwd<T, 0>(a, st, v1, true, a.z, a.bs_z, a.mom, 0, 0);
+    if (rc) return rc;
+  } else
   if (!x_ready && tma_ok && full && ACT == 0 && tma_ptr_ok(a.z, a.bs_z, es) && make_tma_plan(a, 1, 6, &tp5, true)) {
     // sweep 1 forms and stores x itself (MODE 5): no separate add+relu pass
     MrlaLightArgs a5 = a;
@@ -421,7 +452,10 @@ int light_forward_impl(const MrlaLightArgs& a, cudaStream_t st) {
       MRLA_CHECK_LAUNCH();
     }
   // sweep 1
-  if (tma_ok && full) {
+  if (v7p && full) {
+    rc = v7_launch_fwd<T, 0>(a, st, v1, false, a.x, a.bs_x, a.mom, 0, 0);
+    if (rc) return rc;
+  } else if (tma_ok && full) {
     rc = launch_tma_sweep<T, ACT, 0>(a, st, tp1, a.x, a.bs_x, a.o, a.bs_o, nullptr, 0, a.mom);
     if (rc) return rc;
   } else {
@@ -457,7 +491,12 @@ int light_forward_impl(const MrlaLightArgs& a, cudaStream_t st) {
     MRLA_CHECK_LAUNCH();
   }
   // sweep 2
-  if (tma_ok) {
+  if (v7x || v7p) {
+    // walks the batch downwards: the samples sweep 1 read last are the ones still in L2
+    rc = v7x ? v7_launch_fwd<T, 1>(a, st, v2, true, a.z, a.bs_z, nullptr, 1, 1)
+             : v7_launch_fwd<T, 1>(a, st, v2, false, a.x, a.bs_x, nullptr, 1, 0);
+    if (rc) return rc;
+  } else if (tma_ok) {
     rc = launch_tma_sweep<T, ACT, 1>(a, st, tp2, a.x, a.bs_x, a.o, a.bs_o, nullptr, 0, nullptr);
     if (rc) return rc;
   } else {
@@ -485,13 +524,28 @@ int light_backward_impl(const MrlaLightArgs& a, cudaStream_t st) {
                      tma_ptr_ok(a.dy, a.bs_dy, es_) && (a.bs_dx * es_) % 4 == 0 && (a.bs_do * es_) % 4 == 0 &&
                      make_tma_bwd_plan(a, &tpb);
   TmaBwdPlan tpr;
-  const bool tma_r = tma_b && tma_ptr_ok(a.dx, a.bs_dx, es_) && tma_ptr_ok(a.dout, a.bs_do, es_) && make_tma_ring_plan(a, &tpr);
-  if (a.fuse_relu_bwd && !tma_r) return MRLA_ERR_UNSUPPORTED;   // callers ask mrla_light_bwd_fuses_relu() first
-  const int nparts = tma_r ? tpr.maxslots : (tma_b ? tpb.maxslots : pb.grid_y);
-  const size_t need = ((size_t)nparts * a.C * 9 + (size_t)a.B * 2 * a.k_size) * sizeof(float);
+  // ---- v7 sweeps
+  V7Plan va, vb;
+  const bool v7_base = LAYOUT == MRLA_NHWC && HAS_O && ACT == 0 && v7_ptr_ok(a.o, a.bs_o, es_) && v7_ptr_ok(a.dy, a.bs_dy, es_) &&
+                       v7_ptr_ok(a.dx, a.bs_dx, es_) && v7_ptr_ok(a.dout, a.bs_do, es_);
+  const bool v7x = a.x_virtual != 0;
+  if (v7x) {
+    if (!(v7_base && a.fuse_relu_bwd && a.bn_mode == MRLA_BN_TRAIN && a.z && a.z_coef && v7_ptr_ok(a.z, a.bs_z, es_) &&
+          v7_plan(a, V7_SA, true, &va) && v7_plan(a, V7_SB, true, &vb)))
+      return MRLA_ERR_UNSUPPORTED;   // callers ask mrla_light_virtual_x() first
+  }
+  const bool v7p = !v7x && v7_base && !a.fuse_relu_bwd && v7_ptr_ok(a.x, a.bs_x, es_) && v7_plan(a, V7_SA, false, &va) &&
+                   v7_plan(a, V7_SB, false, &vb);
+  const bool v7 = v7x || v7p;
+  const bool tma_r = !v7 && tma_b && tma_ptr_ok(a.dx, a.bs_dx, es_) && tma_ptr_ok(a.dout, a.bs_do, es_) && make_tma_ring_plan(a, &tpr);
+  if (a.fuse_relu_bwd && !tma_r && !v7x) return MRLA_ERR_UNSUPPORTED;   // callers ask mrla_light_bwd_fuses_relu() first
+  const int nparts = v7 ? vb.cpc : (tma_r ? tpr.maxslots : (tma_b ? tpb.maxslots : pb.grid_y));
+  const size_t nfl = (size_t)nparts * a.C * 9 + (size_t)a.B * 2 * a.k_size + (v7x ? (size_t)vb.cpc * 2 * a.C : 0);
+  const size_t need = nfl * sizeof(float);
   if (a.scratch == nullptr || a.scratch_bytes < need) return MRLA_ERR_WORKSPACE;
   float* wv_part = a.scratch;
   float* wqk_part = a.scratch + (size_t)nparts * a.C * 9;
+  float* dz_part = wqk_part + (size_t)a.B * 2 * a.k_size;
   const bool full = (a.bn_mode == MRLA_BN_TRAIN);
   const T* x = static_cast<const T*>(a.x);
   const T* o = static_cast<const T*>(a.o);
@@ -500,10 +554,14 @@ int light_backward_impl(const MrlaLightArgs& a, cudaStream_t st) {
   T* dout = static_cast<T*>(a.dout);
   const int es = a.dtype == MRLA_F32 ? 4 : 2;
   TmaPlan tpa;
-  const bool tma_ok = LAYOUT == MRLA_NHWC && HAS_O && tma_ptr_ok(a.x, a.bs_x, es) && tma_ptr_ok(a.o, a.bs_o, es) &&
+  const bool tma_ok = !v7 && LAYOUT == MRLA_NHWC && HAS_O && tma_ptr_ok(a.x, a.bs_x, es) && tma_ptr_ok(a.o, a.bs_o, es) &&
                       tma_ptr_ok(a.dy, a.bs_dy, es) && make_tma_plan(a, 2, 3, &tpa);
   // sweep A
-  if (tma_ok) {
+  if (v7) {
+    rc = v7x ? v7_launch_fwd<T, 2>(a, st, va, true, a.z, a.bs_z, a.gmom, 0, 0)
+             : v7_launch_fwd<T, 2>(a, st, va, false, a.x, a.bs_x, a.gmom, 0, 0);
+    if (rc) return rc;
+  } else if (tma_ok) {
     rc = launch_tma_sweep<T, ACT, 2>(a, st, tpa, a.x, a.bs_x, a.o, a.bs_o, a.dy, a.bs_dy, a.gmom);
     if (rc) return rc;
   } else {
@@ -538,7 +596,11 @@ int light_backward_impl(const MrlaLightArgs& a, cudaStream_t st) {
     MRLA_CHECK_LAUNCH();
   }
   // sweep B
-  if (tma_r) {
+  if (v7) {
+    rc = v7x ? v7_launch_bwd<T>(a, st, vb, true, true, a.z, a.bs_z, wv_part, dz_part, a.dz_sums)
+             : v7_launch_bwd<T>(a, st, vb, false, false, a.x, a.bs_x, wv_part, nullptr, nullptr);
+    if (rc) return rc;
+  } else if (tma_r) {
     rc = launch_tma_bwd_ring<T, ACT>(a, st, tpr, wv_part);
     if (rc) return rc;
   } else if (tma_b) {
@@ -598,7 +660,14 @@ inline size_t light_bwd_scratch_floats(const MrlaLightArgs& a) {
   TmaBwdPlan tpb;
   if (make_tma_bwd_plan(a, &tpb) && tpb.maxslots > nparts) nparts = tpb.maxslots;
   if (make_tma_ring_plan(a, &tpb) && tpb.maxslots > nparts) nparts = tpb.maxslots;
-  return (size_t)nparts * a.C * 9 + (size_t)a.B * 2 * a.k_size;
+  size_t extra = 0;
+  V7Plan vb;
+  for (int xf = 0; xf < 2; ++xf)
+    if (a.o != nullptr && a.act == MRLA_ACT_NONE && v7_plan(a, V7_SB, xf != 0, &vb)) {
+      if (vb.cpc > nparts) nparts = vb.cpc;
+      extra = (size_t)vb.cpc * 2 * a.C;
+    }
+  return (size_t)nparts * a.C * 9 + (size_t)a.B * 2 * a.k_size + extra;
 }
 
 }  // namespace mrla

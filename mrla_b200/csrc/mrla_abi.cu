@@ -29,7 +29,8 @@ static int check_common(const MrlaLightArgs* a, bool bwd) {
   if (a->layout != MRLA_NCHW && a->layout != MRLA_NHWC) return MRLA_ERR_UNSUPPORTED;
   if (a->act != MRLA_ACT_NONE && a->act != MRLA_ACT_GELU) return MRLA_ERR_UNSUPPORTED;
   if (a->bn_mode < MRLA_BN_NONE || a->bn_mode > MRLA_BN_EVAL) return MRLA_ERR_UNSUPPORTED;
-  if (!a->x || !a->wq || !a->wk || !a->wv || !a->mom || !a->gate || !a->mean || !a->rstd) return MRLA_ERR_NULL;
+  if ((!a->x && !a->x_virtual) || !a->wq || !a->wk || !a->wv || !a->mom || !a->gate || !a->mean || !a->rstd) return MRLA_ERR_NULL;
+  if (a->x_virtual && (!a->z || !a->z_coef || !a->o)) return MRLA_ERR_NULL;
   if (a->o && !a->lam) return MRLA_ERR_NULL;
   if (a->bn_mode != MRLA_BN_NONE && (!a->gamma || (!bwd && !a->beta))) return MRLA_ERR_NULL;
   if (!bwd && a->bn_mode == MRLA_BN_EVAL && (!a->running_mean || !a->running_var)) return MRLA_ERR_NULL;
@@ -102,6 +103,11 @@ int mrla_light_bwd_fuses_relu(const MrlaLightArgs* a) {
 int mrla_light_fwd_folds_bn(const MrlaLightArgs* a) {
   if (a == nullptr) return 0;
   return light_fwd_can_fold_bn(*a) ? 1 : 0;
+}
+
+int mrla_light_virtual_x(const MrlaLightArgs* a) {
+  if (a == nullptr) return 0;
+  return v7_virtual_x_ok(*a) ? 1 : 0;
 }
 
 int mrla_light_forward(const MrlaLightArgs* a, void* stream) {

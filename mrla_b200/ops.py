@@ -97,8 +97,15 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream(dev=None) -> int:
+    """Raw handle of the current stream of `dev` (default: the current device; every op runs under `_on(dev)`)."""
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _on(t: torch.Tensor):
+    """Device guard: kernels, TMA descriptors and scratch allocations must live on the tensor's device, not on whatever
+    torch.cuda.current_device() happens to be (model.to('cuda:1') with current device 0)."""
+    return torch.cuda.device(t.device)
 
 
 def _require_cuda(t: torch.Tensor, name: str):
@@ -140,6 +147,9 @@ launch_counter = {"fwd": 0, "bwd": 0}
 # TMA-ineligible NCHW inputs, and PROMOTE_NCHW = False, use the generic NCHW kernels directly.
 PROMOTE_NCHW = True
 PROMOTE_MIN_ELEMS = 1 << 20
+# bn3-folded tails never materialise x where the library can re-form it in every sweep (tests switch this off to compare
+# against the materialising kernels)
+ALLOW_VIRTUAL_X = True
 
 
 def _to_nhwc(t: torch.Tensor) -> torch.Tensor:
@@ -205,17 +215,19 @@ class _LightTail(torch.autograd.Function):
             vec = 16 // x_c.element_size()
             if (bs_x == n and bs_o == n and (B * n) % vec == 0 and x_c.data_ptr() % 16 == 0
                     and o_c.data_ptr() % 16 == 0):
-                # the library forms x = relu(z + o) itself (inside sweep 1 on the TMA path) and writes it here
-                z_c, x_c = x_c, _empty_like_layout(x_c, layout)
+                # the library forms x = relu(z + o) itself: either on the fly in every sweep (x_virtual, decided below)
+                # or inside sweep 1, which then writes it into a buffer allocated below
+                z_c, x_c = x_c, None
             else:
                 x_c, bs_x = _canon(torch.relu(x_c + o_c), layout)[0], n
+        like = x_c if x_c is not None else z_c
         if out is not None:
             lay = _layout_of(out)
             if lay is None or lay[0] != layout or out.dtype != x.dtype or out.shape != x.shape:
                 raise RuntimeError("mrla_b200: `out` buffer must have the layout / dtype / shape of x")
             y, bs_y = out, lay[1]
         else:
-            y = _empty_like_layout(x_c, layout)
+            y = _empty_like_layout(like, layout)
             bs_y = C * H * W
         dev = x.device
         g = C // cfg.dim_perhead
@@ -237,19 +249,26 @@ class _LightTail(torch.autograd.Function):
         a.residual, a.update_running = int(cfg.residual), int(cfg.update_running and rm is not None)
         a.eps, a.momentum = cfg.eps, cfg.momentum
         a.bs_x, a.bs_o, a.bs_y = bs_x, bs_o, bs_y
-        a.x, a.o, a.y = _ptr(x_c), _ptr(o_c), _ptr(y)
+        a.o, a.y = _ptr(o_c), _ptr(y)
         a.wq, a.wk, a.wv, a.lam = _ptr(wq32), _ptr(wk32), _ptr(wv32), _ptr(lam32)
         a.gamma, a.beta, a.running_mean, a.running_var = _ptr(ga32), _ptr(be32), _ptr(rm), _ptr(rv)
         a.drop_scale = _ptr(ds32)
         a.mom, a.gate, a.mean, a.rstd, a.coef = _ptr(mom), _ptr(gate), _ptr(stats[0]), _ptr(stats[1]), _ptr(coef)
         if z_c is not None:
             a.z, a.bs_z = _ptr(z_c), C * H * W
+        # x is never materialised where the library re-forms it in every sweep (round 2)
+        virtual = (z_c is not None and (z_coef is not None or z_coef_fn is not None) and ALLOW_VIRTUAL_X
+                   and bool(L.mrla_light_virtual_x(ctypes.byref(a))))
+        if z_c is not None and not virtual:
+            x_c = _empty_like_layout(z_c, layout)
+        a.x = _ptr(x_c)
         if z_coef_fn is not None:
-            folds = z_c is not None and bool(L.mrla_light_fwd_folds_bn(ctypes.byref(a)))
+            folds = virtual or (z_c is not None and bool(L.mrla_light_fwd_folds_bn(ctypes.byref(a))))
             z_coef = z_coef_fn(folds, z_c if z_c is not None else x_c)
             ctx.bn3_folded = z_coef is not None
         if z_coef is not None:
             a.z_coef = _ptr(z_coef)
+        a.x_virtual = int(virtual)
         _lib.check(L.mrla_light_forward(ctypes.byref(a), _stream()), "mrla_light_forward")
         _Prof.end("light_fwd", (B, C, H, W, x.dtype, layout, bool(cfg.fuse_add_relu)), ev)
         launch_counter["fwd"] += L.mrla_last_launch_count()
@@ -261,7 +280,10 @@ class _LightTail(torch.autograd.Function):
         ctx.bs = (bs_x, bs_o)
         ctx.param_meta = [(p.shape, p.dtype, p.stride()) if p is not None else None
                           for p in (wq, wk, wv, lam, gamma, beta)]
-        ctx.save_for_backward(x_c, o_c, wq32, wk32, wv32, lam32, ga32, ds32, mom, gate, stats)
+        ctx.virtual = virtual
+        # virtual: the raw conv3 output (alive anyway as bn3's saved input) stands in for x, plus the [2,C] coefficients
+        ctx.save_for_backward(z_c if virtual else x_c, o_c, wq32, wk32, wv32, lam32, ga32, ds32, mom, gate, stats,
+                              z_coef if virtual else None)
         if out is not None:
             ctx.mark_dirty(out)
         return y
@@ -269,8 +291,9 @@ class _LightTail(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         L = _lib.lib()
-        x_c, o_c, wq32, wk32, wv32, lam32, ga32, ds32, mom, gate, stats = ctx.saved_tensors
+        x_c, o_c, wq32, wk32, wv32, lam32, ga32, ds32, mom, gate, stats, z_coef = ctx.saved_tensors
         cfg, layout = ctx.cfg, ctx.layout
+        virtual = ctx.virtual
         B, C, H, W = x_c.shape
         if dy.dtype != x_c.dtype:
             dy = dy.to(x_c.dtype)
@@ -298,7 +321,14 @@ class _LightTail(torch.autograd.Function):
         a.eps, a.momentum = cfg.eps, cfg.momentum
         a.bs_x, a.bs_o = ctx.bs
         a.bs_dy, a.bs_dx, a.bs_do = bs_dy, C * H * W, C * H * W
-        a.x, a.o = _ptr(x_c), _ptr(o_c)
+        a.o = _ptr(o_c)
+        dz_sums = None
+        if virtual:
+            dz_sums = torch.empty((2, C), **f32)
+            a.z, a.bs_z, a.z_coef, a.x_virtual, a.dz_sums = _ptr(x_c), C * H * W, _ptr(z_coef), 1, _ptr(dz_sums)
+        else:
+            a.x = _ptr(x_c)
+        ctx.dz_sums = dz_sums
         a.wq, a.wk, a.wv, a.lam, a.gamma = _ptr(wq32), _ptr(wk32), _ptr(wv32), _ptr(lam32), _ptr(ga32)
         a.drop_scale = _ptr(ds32)
         a.mom, a.gate, a.mean, a.rstd = _ptr(mom), _ptr(gate), _ptr(stats[0]), _ptr(stats[1])
@@ -309,7 +339,7 @@ class _LightTail(torch.autograd.Function):
         a.dgamma = _ptr(dch[1]) if has_bn else None
         a.dbeta = _ptr(dch[2]) if has_bn else None
         a.gmom, a.bcoef = _ptr(gmom), _ptr(bcoef)
-        fused_epilogue = bool(cfg.fuse_add_relu and L.mrla_light_bwd_fuses_relu(ctypes.byref(a)))
+        fused_epilogue = virtual or bool(cfg.fuse_add_relu and L.mrla_light_bwd_fuses_relu(ctypes.byref(a)))
         a.fuse_relu_bwd = int(fused_epilogue)
         nbytes = L.mrla_light_bwd_scratch_bytes(ctypes.byref(a))
         scratch = torch.empty((max(nbytes, 4) + 3) // 4, **f32)
@@ -421,6 +451,7 @@ class _Bn3LightTail(torch.autograd.Function):
         a.eps, a.momentum = eps3, momentum3
         a.x, a.gamma, a.stats, a.coef = _ptr(c3), _ptr(w3_32), _ptr(stats3), _ptr(coef3)
         a.dy, a.dx, a.dgamma, a.dbeta = _ptr(dz), _ptr(dc3), _ptr(dgb[0]), _ptr(dgb[1])
+        a.sums = _ptr(getattr(inner, "dz_sums", None))   # sweep B already reduced sum dz, sum dz*c3 (x_virtual path)
         nbytes = L.mrla_bn_scratch_bytes(ctypes.byref(a))
         scratch = torch.empty((max(nbytes, 4) + 3) // 4, **f32)
         a.scratch, a.scratch_bytes = _ptr(scratch), scratch.numel() * 4

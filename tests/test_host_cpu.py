@@ -129,9 +129,12 @@ def test_bn3_fold_and_pool_host_logic_on_cpu_tensors():
 
 
 def test_light_args_mirror_has_the_producer_fold_fields():
-    """ABI v3: z / bs_z / z_coef close the struct, in the order of include/mrla_b200.h."""
+    """ABI v4: z / bs_z / z_coef / dz_sums close the struct, in the order of include/mrla_b200.h; x_virtual sits in the
+    old reserved slot; MrlaBnArgs ends with the optional precomputed sums."""
     from mrla_b200 import _lib
     names = [f[0] for f in _lib.MrlaLightArgs._fields_]
-    assert names[-4:] == ["scratch_bytes", "z", "bs_z", "z_coef"]
-    assert _lib.ABI_VERSION == 3
-    assert [f[0] for f in _lib.MrlaBnArgs._fields_][6] == "stats_only"
+    assert names[-5:] == ["scratch_bytes", "z", "bs_z", "z_coef", "dz_sums"]
+    assert names[13] == "x_virtual"
+    assert _lib.ABI_VERSION == 4
+    bn = [f[0] for f in _lib.MrlaBnArgs._fields_]
+    assert bn[6] == "stats_only" and bn[-1] == "sums"
