@@ -91,9 +91,8 @@ __device__ __forceinline__ float2 form_x(typename RawPair<T>::type zr, typename 
                                          bool valid) {
   typename RawPair<T>::type z2 = pack_pair<T>(ffma2(za, unpack_pair<T>(zr), zb));
   typename RawPair<T>::type xr = raw_relu<T>(raw_add<T>(z2, ir));
-  float2 x = unpack_pair<T>(xr);
-  if (!valid) x = f2(0.f, 0.f);
-  return x;
+  if (!valid) xr = raw_zero<T>();   // one select on the packed pair
+  return unpack_pair<T>(xr);
 }
 
 // shared-memory header: full barriers at +0, empty barriers at +128 (up to 16 stages each)
@@ -435,39 +434,40 @@ struct V7Bwd {
   int sidx[3];               // pipeline stage that holds row s, per window slot
   float2 xw[3][KX];
   float2 da[3][K];           // dX row accumulators, row h lives in slot h % 3
-  // TMA load cursor (thread 0 only).  There is no producer warp: 8 consumer warps + 1 would be allocated like 12 warps
-  // (registers are granted per 4 warps), which caps a thread at 168 registers; at 256 threads this kernel gets its ~220.
-  bool issuer;
+  // No producer warp (8 consumer warps + 1 would be allocated like 12 warps — registers are granted per 4 warps — which
+  // caps a thread at 168 registers; at 256 threads this kernel gets its ~220).  Stages are refilled by whichever warp
+  // releases them LAST: every warp bumps a per-stage shared counter when it is done with a stage, and the lane whose
+  // increment completes the round requests the row that goes into that stage next (global row + S) on the spot.
   const CUtensorMap* tm_x;
   const CUtensorMap* tm_o;
   const CUtensorMap* tm_dy;
-  int cb, ld_bi, ld_row, ld_st, ld_left;
-  uint32_t ld_ph;
+  int cb, m, rows_total;     // rows_total = rows of all images of this CTA
+  int grow;                  // global index (over the CTA's images) of the row being fetched
+  int gidx[3];               // global row index per window slot
+  uint32_t cnt_s;            // shared address of the per-stage release counters
   uint64_t pol;
 
   __device__ __forceinline__ V7Bwd(const V7Params& P_) : P(P_) {}
   __device__ __forceinline__ bool col_ok(int j) const { return (vmask >> j) & 1u; }
-  __device__ __forceinline__ void release(int sx) {
-    __syncwarp();
-    if (lane == 0) mbar_arrive_s(bar_s + 128 + sx * 8);
+  // request global row g (of this CTA's row sequence) into stage sx
+  __device__ __forceinline__ void issue_row(int g, int sx) {
+    const int img = g / P.H, row = g - img * P.H;
+    const int bi = m + img * P.cpc;
+    const int bb = P.rev ? P.B - 1 - bi : bi;
+    const uint32_t fb = bar_s + sx * 8;
+    const uint32_t dst = stages_s + (uint32_t)sx * P.stage_bytes;
+    mbar_expect_tx_s(fb, P.stage_bytes);
+    tma_load_4d_hint(dst, tm_x, fb, cb * CB, -2, row, bb, pol);
+    tma_load_4d_hint(dst + P.x_bytes, tm_o, fb, cb * CB, XF ? -2 : -1, row, bb, pol);
+    tma_load_4d_hint(dst + P.x_bytes + P.o_bytes, tm_dy, fb, cb * CB, -1, row, bb, pol);
   }
-  // issuer: request the next image row(s) if their stage has been released by every warp (never blocks: the stage may
-  // still be held by this very warp)
-  __device__ __forceinline__ void try_issue() {
-    if (!issuer) return;
-#pragma unroll 1
-    for (int k = 0; k < 2 && ld_left > 0; ++k) {
-      if (!mbar_test_wait_s(bar_s + 128 + ld_st * 8, ld_ph)) break;
-      const int bb = P.rev ? P.B - 1 - ld_bi : ld_bi;
-      const uint32_t fb = bar_s + ld_st * 8;
-      const uint32_t dst = stages_s + (uint32_t)ld_st * P.stage_bytes;
-      mbar_expect_tx_s(fb, P.stage_bytes);
-      tma_load_4d_hint(dst, tm_x, fb, cb * CB, -2, ld_row, bb, pol);
-      tma_load_4d_hint(dst + P.x_bytes, tm_o, fb, cb * CB, XF ? -2 : -1, ld_row, bb, pol);
-      tma_load_4d_hint(dst + P.x_bytes + P.o_bytes, tm_dy, fb, cb * CB, -1, ld_row, bb, pol);
-      if (++ld_st == P.S) { ld_st = 0; ld_ph ^= 1; }
-      if (++ld_row == P.H) { ld_row = 0; ld_bi += P.cpc; }
-      --ld_left;
+  // this warp is done with stage sx, which held global row g
+  __device__ __forceinline__ void release(int sx, int g) {
+    __syncwarp();
+    if (lane == 0) {
+      uint32_t old;
+      asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(cnt_s + sx * 4) : "memory");
+      if (((old + 1) % (uint32_t)P.ncw) == 0 && g + P.S < rows_total) issue_row(g + P.S, sx);
     }
   }
 
@@ -476,15 +476,10 @@ struct V7Bwd {
   __device__ __forceinline__ void step() {
     constexpr int IM1 = (I + 2) % 3;   // slot of row s-1
     constexpr int IM2 = (I + 1) % 3;   // slot of row s-2
-    try_issue();
     if (FETCH) {
-      if (issuer) {
-        // the row may not have been requested yet (its stage was still held by a slower warp): keep trying while waiting
-        while (!mbar_try_wait_s(bar_s + st * 8, ph)) try_issue();
-      } else {
-        mbar_wait_s(bar_s + st * 8, ph);
-      }
+      mbar_wait_s(bar_s + st * 8, ph);
       sidx[I] = st;
+      gidx[I] = grow++;
       const uint32_t xa = stages_s + (uint32_t)st * P.stage_bytes + tbase;
       if (XF) {
         const uint32_t oa = xa + P.x_bytes;
@@ -567,7 +562,7 @@ struct V7Bwd {
           dw[8] = ffma2(t, bot[j + 2], dw[8]);
         }
       }
-      if (!HOLD2) release(sidx[IM1]);
+      if (!HOLD2) release(sidx[IM1], gidx[IM1]);
       // scatter T row t = s-1:  dX[h][w] += wv[i][dj] * T[h-i+1][w-dj+1]
 #pragma unroll
       for (int jo = 0; jo < K; ++jo) {
@@ -625,7 +620,7 @@ struct V7Bwd {
         tma_store_4d(tm_do, src + OROW, ychan, ycol, r - 2, b);
         bulk_commit();
       }
-      if (HOLD2) release(sidx[IM2]);
+      if (HOLD2) release(sidx[IM2], gidx[IM2]);
     }
     ++r;
   }
@@ -692,18 +687,17 @@ k_v7_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUten
   S.bar_s = bar_s;
   S.stages_s = stages_s;
   S.lane = threadIdx.x & 31;
-  S.issuer = (ct == 0);
   S.cb = cb;
-  S.ld_bi = m;
-  S.ld_row = 0;
-  S.ld_st = 0;
-  S.ld_ph = 1;   // first pass over the ring: slots are free
-  S.ld_left = n_my * P.H;
+  S.m = m;
+  S.rows_total = n_my * P.H;
+  S.grow = 0;
+  S.gidx[0] = S.gidx[1] = S.gidx[2] = 0;
+  S.cnt_s = bar_s + 128;   // the release counters live where the forward kernels keep their empty barriers
   S.pol = l2_policy_evict_first();
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.S; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], P.ncw);
+      reinterpret_cast<uint32_t*>(empty)[s] = 0u;
     }
     mbar_fence_init();
     tma_prefetch_desc(&tm_x);
@@ -713,8 +707,8 @@ k_v7_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUten
     tma_prefetch_desc(&tm_do);
   }
   __syncthreads();
-  if (S.issuer)
-    for (int s = 0; s < P.S; s += 2) S.try_issue();   // fill the pipeline
+  if (threadIdx.x == 0)
+    for (int s = 0; s < P.S && s < S.rows_total; ++s) S.issue_row(s, s);   // fill the pipeline
   S.tbase = (uint32_t)(q * K) * Bk::CS + (uint32_t)p * 2 * ES;
   S.obuf = smem_u32(tail) + (uint32_t)warp * (3 * 2 * Bk::OROW) + (uint32_t)S.lane * 2 * ES;
   S.ycol = q * K;
