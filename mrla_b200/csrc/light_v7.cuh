@@ -94,6 +94,17 @@ __device__ __forceinline__ float2 form_x(typename RawPair<T>::type zr, typename 
   if (!valid) xr = raw_zero<T>();   // one select on the packed pair
   return unpack_pair<T>(xr);
 }
+// same with the column's validity as DATA (all ones / zero): one AND, no predicate logic in the row loop
+__device__ __forceinline__ uint32_t raw_and(uint32_t a, uint32_t m) { return a & m; }
+__device__ __forceinline__ float2 raw_and(float2 a, uint32_t m) {
+  return make_float2(__uint_as_float(__float_as_uint(a.x) & m), __uint_as_float(__float_as_uint(a.y) & m));
+}
+template <typename T>
+__device__ __forceinline__ float2 form_x_m(typename RawPair<T>::type zr, typename RawPair<T>::type ir, float2 za, float2 zb,
+                                           uint32_t m) {
+  typename RawPair<T>::type z2 = pack_pair<T>(ffma2(za, unpack_pair<T>(zr), zb));
+  return unpack_pair<T>(raw_and(raw_relu<T>(raw_add<T>(z2, ir)), m));
+}
 
 // shared-memory header: full barriers at +0, empty barriers at +128 (up to 16 stages each)
 constexpr int kV7Hdr = 256;
@@ -150,6 +161,7 @@ struct V7Fwd {
   uint32_t obuf;             // this warp's staging rows (2 buffers), lane offset included
   int lane, ycol, ychan;     // TMA store coordinates of the warp (first own column, first channel)
   uint32_t vmask;            // bit j: window column j lies inside the image
+  uint32_t em0, em1;         // validity of the two halo columns as data (all ones / zero)
   float2 w9[9], za, zb;
   float2 cA, cL, cD;
   float2 acc[NACC > 0 ? NACC : 1], accb[NACC > 0 ? NACC : 1];
@@ -174,8 +186,10 @@ struct V7Fwd {
         for (int j = 0; j < KW; ++j) {
           const Raw zr = lds_raw<T>(xa + j * CS);
           const Raw ir = lds_raw<T>(oa + j * CS);
-          const bool edge = RAGGED || j == 0 || j == KW - 1;
-          win[I][j] = form_x<T>(zr, ir, za, zb, edge ? col_ok(j) : true);
+          if (RAGGED) win[I][j] = form_x<T>(zr, ir, za, zb, col_ok(j));
+          else if (j == 0) win[I][j] = form_x_m<T>(zr, ir, za, zb, em0);
+          else if (j == KW - 1) win[I][j] = form_x_m<T>(zr, ir, za, zb, em1);
+          else win[I][j] = form_x<T>(zr, ir, za, zb, true);
           if (j >= 1 && j <= K) oc[I][j - 1] = ir;
         }
       } else {
@@ -343,6 +357,8 @@ k_v7_fwd(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUten
     const int col = q * K - 1 + j;
     if (col >= 0 && col < P.W) S.vmask |= 1u << j;
   }
+  S.em0 = S.col_ok(0) ? 0xffffffffu : 0u;
+  S.em1 = S.col_ok(F::KW - 1) ? 0xffffffffu : 0u;
   S.st = 0;
   S.ph = 0;
   S.ob = 0;
@@ -425,6 +441,8 @@ struct V7Bwd {
   uint32_t obuf;             // this warp's staging: [3 rows][dx row | do row], lane offset included
   int lane, ycol, ychan;
   uint32_t vmask;            // bit j: x-window column j (image column q*K-2+j) lies inside the image
+  uint32_t em[4];            // the same as data for the four window columns that can fall outside (0, 1, KX-2, KX-1)
+  float2 tm0, tm1;           // 1 / 0 for the two T halo columns
   float2 w9[9], za, zb, lm;
   float2 q0, q1, q2, q3, ta, dyc;
   float2 dw[9];
@@ -487,8 +505,10 @@ struct V7Bwd {
         for (int j = 0; j < KX; ++j) {
           const Raw zr = lds_raw<T>(xa + j * CS);
           const Raw ir = lds_raw<T>(oa + j * CS);
-          const bool edge = RAGGED || j < 2 || j >= KX - 2;
-          xw[I][j] = form_x<T>(zr, ir, za, zb, edge ? col_ok(j) : true);
+          if (RAGGED) xw[I][j] = form_x<T>(zr, ir, za, zb, col_ok(j));
+          else if (j < 2) xw[I][j] = form_x_m<T>(zr, ir, za, zb, j == 0 ? em[0] : em[1]);
+          else if (j >= KX - 2) xw[I][j] = form_x_m<T>(zr, ir, za, zb, j == KX - 2 ? em[2] : em[3]);
+          else xw[I][j] = form_x<T>(zr, ir, za, zb, true);
         }
       } else {
 #pragma unroll
@@ -541,8 +561,13 @@ struct V7Bwd {
         ds = ffma2(q2, u[j], ds);
         ds = ffma2(q3, ov, ds);
         float2 t = fmul2(ta, ds);
-        const bool edge = RAGGED || j == 0 || j == KT - 1;
-        if (edge && !col_ok(j + 1)) t = f2(0.f, 0.f);
+        if (RAGGED) {
+          if (!col_ok(j + 1)) t = f2(0.f, 0.f);
+        } else if (j == 0) {
+          t = fmul2(t, tm0);
+        } else if (j == KT - 1) {
+          t = fmul2(t, tm1);
+        }
         tt[j] = t;
         if (j >= 1 && j <= K) {
           const int jo = j - 1;
@@ -719,6 +744,12 @@ k_v7_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUten
     const int col = q * K - 2 + j;
     if (col >= 0 && col < P.W) S.vmask |= 1u << j;
   }
+  S.em[0] = S.col_ok(0) ? 0xffffffffu : 0u;
+  S.em[1] = S.col_ok(1) ? 0xffffffffu : 0u;
+  S.em[2] = S.col_ok(Bk::KX - 2) ? 0xffffffffu : 0u;
+  S.em[3] = S.col_ok(Bk::KX - 1) ? 0xffffffffu : 0u;
+  S.tm0 = S.col_ok(1) ? f2(1.f, 1.f) : f2(0.f, 0.f);
+  S.tm1 = S.col_ok(Bk::KX - 2) ? f2(1.f, 1.f) : f2(0.f, 0.f);
   S.st = 0;
   S.ph = 0;
   S.sidx[0] = S.sidx[1] = S.sidx[2] = 0;

@@ -1,8 +1,9 @@
 """GPU: the bottleneck's bn3 folded into the MRLA-light tail op (one autograd node: BatchNorm statistics -> sweep 1 applies
 a_c*conv3 + b_c, adds the identity, ReLUs, takes the moments) against the same block with bn3 as its own op — SURVEY.md
-§8f rank 1, reference resnet/models/resnet_mrla_light.py:101-102,113-116.  The two paths run the same arithmetic on the
-same values, so outputs, every gradient and the BatchNorm buffers must agree bit for bit; the oracle comparison of the
-whole block / model (test_model_gpu.py) covers parity with the reference itself."""
+§8f rank 1, reference resnet/models/resnet_mrla_light.py:101-102,113-116.  The two paths run the same arithmetic per
+element (x is formed in storage precision either way) with different summation orders, so outputs, gradients and the
+BatchNorm buffers agree to accumulation rounding; parity with the reference itself is tests/test_v7_gpu.py (fp64 oracle of
+the folded op at the BASELINE shapes) and test_model_gpu.py (whole model)."""
 import copy
 
 import pytest
@@ -63,14 +64,18 @@ def test_bn3_fold_equals_separate_bn3(shape, dtype, monkeypatch):
                      {n: b.clone() for n, b in blk.named_buffers()}))
     assert used["fold"] == 1, "the folded path did not run"
     (ya, dxa, ga, ba), (yb, dxb, gb, bb) = outs
-    assert torch.equal(ya, yb)
-    assert torch.equal(dxa, dxb)
+    # round 2: the folded op re-forms x inside every sweep (7-column threads, different summation order of the moments
+    # and of the BatchNorm reductions), so the two paths agree to accumulation rounding instead of bit for bit
+    from conftest import rel_err
+    tol = 2e-5 if dtype == torch.float32 else 1e-2
+    assert rel_err(ya, yb) < tol
+    assert rel_err(dxa, dxb) < tol
     for n in ga:
         assert (ga[n] is None) == (gb[n] is None), n
         if ga[n] is not None:
-            assert torch.equal(ga[n], gb[n]), n
+            assert rel_err(ga[n], gb[n]) < 2 * tol, n
     for n in ba:
-        assert torch.equal(ba[n], bb[n]), n
+        assert rel_err(ba[n].float(), bb[n].float()) < 1e-5, n
 
 
 def test_bn3_fold_not_used_in_eval_or_nchw():

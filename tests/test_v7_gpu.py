@@ -73,7 +73,7 @@ def _run_product(c3, idt, dy, P, ds, k, d=32):
     return y.detach(), c3g.grad, idg.grad, grads, dict(rm=rm, rv=rv, rm3=bn3.running_mean.clone(), rv3=bn3.running_var.clone())
 
 
-def _run_oracle(c3, idt, dy, P, ds, d=32):
+def _run_oracle(c3, idt, dy, P, ds, d=32, storage_dtype=None):
     from oracle import mrla_oracle as O
     C = c3.shape[1]
     dev = c3.device
@@ -82,7 +82,8 @@ def _run_oracle(c3, idt, dy, P, ds, d=32):
     Pd = {n: v.detach().double().requires_grad_() for n, v in P.items()}
     y, ex = O.bottleneck_light_tail(c3d, idd, Pd["w3"], Pd["b3"], torch.zeros(C, **f64), torch.ones(C, **f64), Pd["wq"],
                                     Pd["wk"], Pd["wv"], Pd["lam"], C // d, Pd["gamma"], Pd["beta"], torch.zeros(C, **f64),
-                                    torch.ones(C, **f64), drop_scale=None if ds is None else ds.double())
+                                    torch.ones(C, **f64), drop_scale=None if ds is None else ds.double(),
+                                    storage_dtype=storage_dtype)
     y.backward(dy.double())
     out = (y.detach(), c3d.grad, idd.grad, {n: v.grad for n, v in Pd.items()}, ex)
     return out
@@ -99,12 +100,15 @@ def test_bn3_tail_virtual_x_vs_oracle(C, HW, dtype, B, cuda_device):
     calls0 = dict(ops.launch_counter)
     y, dc3, did, grads, bufs = _run_product(c3, idt, dy, P, ds, k)
     assert ops.launch_counter["fwd"] > calls0["fwd"]
-    yr, dc3r, didr, gr, ex = _run_oracle(c3, idt, dy, P, ds)
+    # bf16: the oracle stores the bn3 output and the sum in bf16 like the reference's autocast graph does (which side of
+    # the ReLU an element near the kink falls on is decided by those two roundings); everything else is fp64
+    yr, dc3r, didr, gr, ex = _run_oracle(c3, idt, dy, P, ds, storage_dtype=None if dtype == torch.float32 else dtype)
     tol = TOL[dtype]
     assert rel_err(y, yr) < tol
-    # away from the ReLU kink (pre-activation below the storage rounding noise of its operands)
-    # the bn3 output is rounded to the storage dtype before the add (half an ulp of |z|); twice that is excluded
-    eps_store = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -22
+    # elements still excluded: the product's fp32 BatchNorm statistics differ from fp64 ones in the last bits, which can
+    # move a bn3 output across a rounding boundary of the storage dtype and, if the sum is within one ulp of zero, flip
+    # the mask (a handful of elements in 2e8)
+    eps_store = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -22     # two ulps of the stored bn3 output
     keep = (ex["pre"].abs() > eps_store * ex["z"].abs() + 1e-30)
     assert keep.double().mean().item() > 0.99
     assert _masked_rel_err(dc3, dc3r, keep) < tol
