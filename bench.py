@@ -3,6 +3,8 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # product arm (CUDA kernels via the C ABI)
     python bench.py --impl reference [--steps K] [--warmup W]       # reference arm: the reference's CPU path
+    python bench.py --config mrlab|deit_tail|effnet_tail            # the secondary BASELINE configs[2..4] (own JSON line)
+    python bench.py --compile-baseline                              # adds torch.compile to the same-GPU eager baseline
 
 One "step" = forward + loss + backward + SGD update of `resnet50_mrlal` on one synthetic batch
 (256 x 3 x 224 x 224 per GPU, bf16 autocast, channels_last, random-init weights, drop_path 0.2 as
@@ -118,6 +120,7 @@ def cpu_reference_run(steps: int, warmup: int, batch: int = 0):
         if i >= warmup:
             times.append(dt)
     total = sum(times)
+    med = statistics.median(times)
     cpu_name = ""
     try:
         for line in open("/proc/cpuinfo"):
@@ -127,7 +130,8 @@ def cpu_reference_run(steps: int, warmup: int, batch: int = 0):
     except Exception:
         pass
     return dict(img_per_s=batch * len(times) / total, ms_per_step=1e3 * total / len(times), cores=cores,
-                threads=torch.get_num_threads(), cpu=cpu_name, batch=batch)
+                threads=torch.get_num_threads(), cpu=cpu_name, batch=batch, img_per_s_median=batch / med,
+                ms_median=1e3 * med, iters=len(times))
 
 
 def run_reference_arm(args):
@@ -202,9 +206,54 @@ def measure_tail_group(B, C, HW, dev, iters=10, bn3=True):
     return out[0], out[1]
 
 
+def gpu_eager_run(dev, B, steps, warmup, drop_path, compiled=False):
+    """SURVEY.md §2.2's real bar: eager PyTorch running the reference graph on the SAME B200 — the oracle port of
+    resnet50_mrlal (the reference's own ~14 ATen calls per tail; /root/reference does not travel to the GPU box), bf16
+    autocast, channels_last, SGD, same batch.  `compiled`: the same model through torch.compile (inductor)."""
+    from oracle.resnet_oracle import resnet50_mrlal_oracle
+    torch.manual_seed(0)
+    model = resnet50_mrlal_oracle(drop_path=drop_path).to(dev).to(memory_format=torch.channels_last).train()
+    opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
+    crit = nn.CrossEntropyLoss().to(dev)
+    net = torch.compile(model) if compiled else model
+    img = torch.randn(B, 3, 224, 224, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    lbl = torch.randint(0, 1000, (B,), device=dev)
+
+    def step():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = net(img)
+        loss = crit(out.float(), lbl)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del model, net, opt
+    torch.cuda.empty_cache()
+    return dict(img_per_s=B / (ms / 1e3), ms_per_step=ms)
+
+
+def traffic_record():
+    """Measured DRAM bytes of the stage-1 tail op (ncu --set full, tools/profile_v7.sh) with the commit it was taken at."""
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(tpath))
+    except Exception:
+        return {}
+
+
 def run_product_arm(args):
     from mrla_b200 import ops
-    from mrla_b200.resnet_mrla_light import resnet50_mrlal
+    from mrla_b200.train import GraphedStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -218,7 +267,13 @@ def run_product_arm(args):
     B = args.batch
     torch.manual_seed(0)
     torch.backends.cudnn.benchmark = True
-    model = resnet50_mrlal(drop_path=args.drop_path).to(dev).to(memory_format=torch.channels_last).train()
+    if args.config == "mrlab":
+        from mrla_b200.resnet_mrla_base import resnet50_mrlab as factory
+        metric, model_name = "resnet50_mrlab_train_images_per_sec", "resnet50_mrlab"
+    else:
+        from mrla_b200.resnet_mrla_light import resnet50_mrlal as factory
+        metric, model_name = METRIC, "resnet50_mrlal"
+    model = factory(drop_path=args.drop_path).to(dev).to(memory_format=torch.channels_last).train()
     opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)  # reference train.py:199
     net = model
     if world > 1 and args.no_graph:   # eager path: the reference's DDP wrap; the graph path all-reduces a flat buffer
@@ -266,72 +321,23 @@ def run_product_arm(args):
         step(dev_img, dev_lbl)
     barrier()
 
-    # ---- CUDA graphs (static buffers): graph A = forward + loss + backward into ONE flat fp32 gradient buffer,
-    # [N > 1: one NCCL all-reduce (AVG) of that buffer over NVLink/NVSwitch], graph B = SGD update.
-    # The step is ~800 kernel launches and the Python/launch path alone costs ~34 ms per step on this host, which
-    # would cap a ~36 ms GPU step; the reference's DDP (train.py:174) is replaced by the explicit all-reduce of the
-    # same gradients (103 MB fp32, ~0.3 ms at NVLink bandwidth, so overlap with backward is not needed).
-    graph_a = graph_b = None
-    static_loss = None
+    # ---- the product's graphed step (mrla_b200.train.GraphedStep): graph A = forward + loss + backward into ONE flat
+    # fp32 gradient buffer with the bucketed NCCL all-reduce (AVG) overlapped with backward INSIDE the graph,
+    # graph B = SGD update.  Replaces the reference's eager loop + DDP wrap (train.py:172-174, 387-409).
+    gstep = None
     launches_per_step = None
-    flat = None
     if not args.no_graph:
-        params = [p_ for p_ in model.parameters() if p_.requires_grad]
-        flat = torch.zeros(sum(p_.numel() for p_ in params), dtype=torch.float32, device=dev)
-
-        def grad_view(p_, seg):
-            if p_.dim() == 4 and not p_.is_contiguous() and p_.is_contiguous(memory_format=torch.channels_last):
-                k_, c_, r_, s_ = p_.shape
-                return seg.view(k_, r_, s_, c_).permute(0, 3, 1, 2)   # same strides as the channels_last weight
-            return seg.view(p_.shape)
-
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            if world > 1:
-                for p_ in model.parameters():
-                    dist.broadcast(p_.data, 0)
-                for b_ in model.buffers():
-                    dist.broadcast(b_.data, 0)
-            opt.zero_grad(set_to_none=True)
-            off = 0
-            for p_ in params:
-                p_.grad = grad_view(p_, flat[off:off + p_.numel()])
-                off += p_.numel()
-            for _ in range(3):   # warm-up of the exact captured sequence on the capture stream
-                flat.zero_()
-                with torch.autocast("cuda", dtype=torch.bfloat16):
-                    out = model(dev_img)
-                crit(out.float(), dev_lbl).backward()
-                if world > 1:
-                    dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-                opt.step()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
         l0 = ops.launch_counter["fwd"] + ops.launch_counter["bwd"]
-        graph_a, graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph_a):
-            flat.zero_()
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                out = model(dev_img)
-            static_loss = crit(out.float(), dev_lbl)
-            static_loss.backward()
-        with torch.cuda.graph(graph_b, pool=graph_a.pool()):
-            opt.step()
-        launches_per_step = ops.launch_counter["fwd"] + ops.launch_counter["bwd"] - l0
-        torch.cuda.synchronize()
+        gstep = GraphedStep(model, opt, crit, dev_img, dev_lbl, warmup=3, overlap=args.overlap_comm)
+        # launches of one captured step = (warm-up + capture) launches / their count
+        launches_per_step = (ops.launch_counter["fwd"] + ops.launch_counter["bwd"] - l0) // 4
+        dev_img, dev_lbl = gstep.inputs, gstep.targets
     barrier()
 
     def run_step():
-        if graph_a is not None:
-            graph_a.replay()
-            if world > 1:
-                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-            graph_b.replay()
-            return static_loss
+        if gstep is not None:
+            return gstep()
         return step(dev_img, dev_lbl)
-
-    graph = graph_a
 
     # ---- timed region 1: inputs resident in HBM ----
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -347,8 +353,24 @@ def run_product_arm(args):
     torch.cuda.profiler.stop()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = (launches_per_step * K) if graph is not None else (ops.launch_counter["fwd"] + ops.launch_counter["bwd"] - l0)
+    launches = (launches_per_step * K) if gstep is not None else (ops.launch_counter["fwd"] + ops.launch_counter["bwd"] - l0)
     clocks = sampler.stop() if sampler else None
+
+    # ---- device time of the gradient exchange alone (the buckets of the flat buffer, back to back on one stream) ----
+    collective_ms = None
+    if world > 1 and gstep is not None:
+        for _ in range(2):
+            for s_, e_, _ in gstep.buckets:
+                dist.all_reduce(gstep.flat[s_:e_], op=dist.ReduceOp.AVG)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            for s_, e_, _ in gstep.buckets:
+                dist.all_reduce(gstep.flat[s_:e_], op=dist.ReduceOp.AVG)
+        c1.record()
+        torch.cuda.synchronize()
+        collective_ms = max_over_ranks(c0.elapsed_time(c1) / 5)
 
     # ---- timed region 2 (e2e): pinned host batch -> H2D every step, loss read back every step ----
     copy_stream = torch.cuda.Stream()
@@ -374,12 +396,11 @@ def run_product_arm(args):
         img, lbl, ev = slots[i % 2]
         torch.cuda.current_stream().wait_event(ev)
         img.record_stream(torch.cuda.current_stream())
-        if graph is not None:
-            dev_img.copy_(img)      # the graph reads its static input buffers
-            dev_lbl.copy_(lbl)
+        if gstep is not None:
+            gstep.load(img, lbl)      # the graph reads its static input buffers
         if i + 1 < K:
             prefetch(i + 1)
-        loss = run_step() if graph is not None else step(img, lbl)
+        loss = run_step() if gstep is not None else step(img, lbl)
         host_loss[i % 2].copy_(loss.detach(), non_blocking=True)   # D2H read of this step's result
         done = torch.cuda.Event()
         done.record()
@@ -399,7 +420,7 @@ def run_product_arm(args):
     # between two CUDA events on the launching stream: pure device time of the kernel group, independent of how
     # fast the host can enqueue (operands are 3 x 0.4 GB at stage 1, far beyond L2, so every replay is cold).
     tail_times = {}
-    if rank == 0:
+    if rank == 0 and args.config == "mrlal":
         for (C, HW), nblk in STAGE_BLOCKS.items():
             tail_times[(C, HW)] = measure_tail_group(B, C, HW, dev)
     barrier()
@@ -409,68 +430,187 @@ def run_product_arm(args):
         return
 
     peak, peak_kind = peaks()
-    per_shape, tot_bytes, tot_ms = {}, 0.0, 0.0
-    for (C, HW), (f_ms, b_ms) in tail_times.items():
-        nbytes = 9.0 * B * C * HW * HW * 2   # folded op, bf16: fwd R z,id W x,y ; bwd R dy,x,id W dz,d_id
-        per_shape[(C, HW)] = dict(fwd_ms=f_ms, bwd_ms=b_ms, bytes=nbytes, gbs=nbytes / (f_ms + b_ms) / 1e6)
-        tot_bytes += STAGE_BLOCKS[(C, HW)] * nbytes
-        tot_ms += STAGE_BLOCKS[(C, HW)] * (f_ms + b_ms)
     roof = None
-    if (256, 56) in per_shape:
+    if tail_times:
+        per_shape, tot_bytes, tot_ms = {}, 0.0, 0.0
+        for (C, HW), (f_ms, b_ms) in tail_times.items():
+            # 8*N*sizeof — fwd R c3,id W y ; bwd R dy,c3,id W d(c3-side),d(id).  x = relu(bn3(c3)+id) is
+            # never materialised (round 2), so the op's algorithmic bytes ARE the survey's 8 N; round 1 stored x (9 N).
+            nbytes = 8.0 * B * C * HW * HW * 2
+            per_shape[(C, HW)] = dict(fwd_ms=f_ms, bwd_ms=b_ms, bytes=nbytes, gbs=nbytes / (f_ms + b_ms) / 1e6)
+            tot_bytes += STAGE_BLOCKS[(C, HW)] * nbytes
+            tot_ms += STAGE_BLOCKS[(C, HW)] * (f_ms + b_ms)
         d = per_shape[(256, 56)]
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get("stage1_tail_fwd_bwd_dram_bytes")
-            except Exception:
-                traffic = None
+        tr = traffic_record()
         roof = {"bound": "hbm", "achieved": round(d["gbs"], 1), "peak": peak, "unit": "GB/s",
-                "frac": round(d["gbs"] / peak, 4), "traffic": traffic,
+                "frac": round(d["gbs"] / peak, 4), "traffic": tr.get("stage1_tail_fwd_bwd_dram_bytes"),
+                "traffic_source": {k_: tr.get(k_) for k_ in ("measured_at_commit", "file", "how") if k_ in tr},
+                "frac_on_round1_9N_basis": round(d["gbs"] * 9.0 / 8.0 / peak, 4),
+                "frac_of_nominal_8TBps": round(d["gbs"] / 8000.0, 4),
                 "kernel": "MRLA-light block tail fwd+bwd kernel group with the bottleneck's bn3 affine and residual "
-                          "add+ReLU folded in, stage-1 shape (B,256,56,56) bf16 NHWC (sweep 1 = bn3 affine + add + ReLU + "
-                          "moments, cluster mid kernel, sweep 2 / sweep A, cluster mid + gate kernels, sweep B, finish); "
-                          "algorithmic bytes 9*N*2 per block (fwd R z,id W x,y; bwd R dy,x,id W dz,d_id)",
+                          "add+ReLU folded in and x never materialised, stage-1 shape (B,256,56,56) bf16 NHWC (sweep 1 = "
+                          "re-form x + moments, cluster mid kernel, sweep 2; sweep A, cluster mid + gate kernels, sweep B "
+                          "incl. bn3's backward sums, finish); algorithmic bytes 8*N*2 per block (fwd R c3,id W y; bwd R "
+                          "dy,c3,id W d_c3side,d_id) = SURVEY.md 8(d)",
                 "peak_kind": peak_kind,
                 "launch_ms": {"fwd": round(d["fwd_ms"], 4), "bwd": round(d["bwd_ms"], 4)},
                 "how": "the op's forward / backward kernel groups captured in CUDA graphs and replayed 10x between CUDA "
-                       "events on the launching stream, same shapes/dtype/layout as the model's calls; stage-1 operands "
+                       "events on the launching stream, same shapes/dtype/layout as the model's calls, inputs randn (the "
+                       "post-ReLU sparsity of the real identity does not change the bytes moved); stage-1 operands "
                        "(3 x 0.41 GB) exceed L2, stages 3-4 are partially L2-resident as they are inside the model",
                 "all_16_tails": {"ms_per_step": round(tot_ms, 3), "alg_GB_per_step": round(tot_bytes / 1e9, 3),
                                  "achieved": round(tot_bytes / tot_ms / 1e6, 1) if tot_ms else None,
                                  "frac": round(tot_bytes / tot_ms / 1e6 / peak, 4) if tot_ms else None},
                 "per_stage": {f"{c}x{h}x{h}": {"fwd_ms": round(v["fwd_ms"], 4), "bwd_ms": round(v["bwd_ms"], 4),
-                                               "GBps": round(v["gbs"], 1)} for (c, h), v in per_shape.items()}}
+                                               "GBps": round(v["gbs"], 1), "frac": round(v["gbs"] / peak, 4)}
+                              for (c, h), v in per_shape.items()}}
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(steps=2, warmup=1)
-        cpu = {"value": round(r["img_per_s"], 3), "unit": "img/s", "cores": r["threads"], "kind": "port",
+    if world == 1 and not args.no_cpu_baseline and args.config == "mrlal":
+        r = cpu_reference_run(steps=3, warmup=1)
+        cpu = {"value": round(r["img_per_s_median"], 3), "unit": "img/s", "cores": r["threads"], "kind": "port",
                "sample": f"oracle port of reference resnet50_mrlal fwd+bwd, batch {r['batch']} x3x224x224 fp32 "
-                         f"(BASELINE configs[0]), 2 timed + 1 warm-up iterations, {r['ms_per_step']:.0f} ms/iter, {r['cpu']}"}
+                         f"(BASELINE configs[0]), median of {r['iters']} timed iterations after 1 warm-up, "
+                         f"{r['ms_median']:.0f} ms/iter, {r['cpu']}"}
+    eager = None
+    if world == 1 and not args.no_eager_baseline and args.config == "mrlal":
+        # the GPU memory of the product model is still held: free what the graphs do not need first
+        torch.cuda.empty_cache()
+        try:
+            r = gpu_eager_run(dev, B, steps=5, warmup=3, drop_path=args.drop_path)
+            eager = {"value": round(r["img_per_s"], 1), "unit": "img/s", "ms_per_step": round(r["ms_per_step"], 2),
+                     "what": "oracle port of the reference resnet50_mrlal (its own ATen call sequence) on the same B200: eager "
+                             "PyTorch, bf16 autocast, channels_last, SGD, same per-GPU batch; 5 timed steps after 3 warm-up"}
+            if args.compile_baseline:
+                rc = gpu_eager_run(dev, B, steps=5, warmup=3, drop_path=args.drop_path, compiled=True)
+                eager["torch_compile"] = {"value": round(rc["img_per_s"], 1), "ms_per_step": round(rc["ms_per_step"], 2)}
+        except Exception as exc:   # out of memory next to the captured graphs, inductor missing a toolchain, ...
+            eager = {"unavailable": repr(exc)[:200]}
     line = {
-        "metric": METRIC, "value": round(world * B * K / (ms / 1e3), 2), "unit": "img/s", "n_gpus": world,
+        "metric": metric, "value": round(world * B * K / (ms / 1e3), 2), "unit": "img/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "resnet50_mrlal training step (fwd+loss+bwd+SGD), BASELINE configs[1]",
-                   "model": "resnet50_mrlal", "per_gpu_batch": B, "global_batch": B * world, "image": "3x224x224",
+        "config": {"workload": f"{model_name} training step (fwd+loss+bwd+SGD), BASELINE configs[{2 if args.config == 'mrlab' else 1}]",
+                   "model": model_name, "per_gpu_batch": B, "global_batch": B * world, "image": "3x224x224",
                    "precision": "bf16 autocast, fp32 master weights", "memory_format": "channels_last",
                    "drop_path": args.drop_path,
                    "host_batch": "e2e: pinned uint8 HWC images + int64 labels copied H2D every step, normalised to bf16 "
                                  "channels_last on the device",
-                   "parallelism": f"dp{world}" + ((" (flat-gradient NCCL all-reduce)" if graph is not None else " (DDP/NCCL)")
-                                                  if world > 1 else ""),
+                   "parallelism": f"dp{world}" + ((" (flat-gradient NCCL all-reduce captured in the step graph" +
+                                                   (", bucketed and overlapped with backward)" if args.overlap_comm else ")")
+                                                   if gstep is not None else " (DDP/NCCL)") if world > 1 else ""),
                    "l2": "inputs exceed L2 (per-step activations >> 126 MB); no explicit flush",
-                   "launch": "CUDA graphs (fwd+bwd | all-reduce | SGD)" if graph is not None else "eager launches"},
+                   "launch": "mrla_b200.train.GraphedStep: CUDA graphs (fwd+bwd+all-reduce | SGD)" if gstep is not None
+                             else "eager launches"},
         "clocks": clocks,
         "e2e": {"value": round(world * B * K / (ms_e2e / 1e3), 2), "unit": "img/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / K, 3), "last_loss": round(last_loss, 4)},
         "gpu_launches": launches,
         "roofline": roof,
         "cpu_baseline": cpu,
+        "gpu_eager_baseline": eager,
     }
+    if collective_ms is not None:
+        line["collective_ms"] = round(collective_ms, 4)
+        line["collective"] = {"buckets": len(gstep.buckets), "bytes": int(gstep.flat.numel() * 4),
+                              "what": "device time of the bucketed gradient all-reduce (AVG, fp32) run alone; inside the "
+                                      "step it overlaps backward"}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------ secondary configs
+def _time_fn(fn, iters=20, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def run_tail_config(args):
+    """--config deit_tail / effnet_tail: BASELINE configs[4] / [3] at the module level (SURVEY.md 8d metric 3): device
+    time of the MRLA tail fwd+bwd at the model's shapes, algorithmic GB/s on 8*N*sizeof, next to eager PyTorch running the
+    oracle restatement (the reference's ATen sequence) on the same GPU."""
+    from mrla_b200 import _lib
+    from mrla_b200.ops import LightCfg, light_tail
+    from oracle import mrla_oracle as O
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    peak, peak_kind = peaks()
+    bf = torch.bfloat16
+    rows = {}
+    tot_bytes = tot_ms = tot_eager = 0.0
+    if args.config == "deit_tail":
+        from mrla_b200.deit_mrla_light import mrlal_module
+        B = args.batch
+        mod = mrlal_module(192, 16).to(dev).to(bf)
+        x = torch.randn(B, 197, 192, device=dev, dtype=bf).requires_grad_()
+        o = torch.randn(B, 197, 192, device=dev, dtype=bf).requires_grad_()
+        dy = torch.randn(B, 197, 192, device=dev, dtype=bf)
+        P = dict(mod.named_parameters())
+
+        def mine():
+            y = x + mod(x, o)
+            y.backward(dy)
+
+        def eager():
+            y = O.deit_light_block_tail(x, o, P["mrla.Wq.weight"], P["mrla.Wk.weight"], P["mrla.Wv.weight"], P["lambda_t"],
+                                        12, P["normx.weight"], P["normx.bias"], P["normo.weight"], P["normo.bias"])
+            y.backward(dy)
+
+        t_m, t_e = _time_fn(mine), _time_fn(eager)
+        nbytes = 8.0 * B * 197 * 192 * 2
+        rows["256x197x192"] = dict(ms=round(t_m, 4), eager_ms=round(t_e, 4), GBps=round(nbytes / t_m / 1e6, 1))
+        tot_bytes, tot_ms, tot_eager = 12 * nbytes, 12 * t_m, 12 * t_e
+        metric, unit, value = "deit_mrlal_tiny_mrla_tails_ms_per_step", "ms", 12 * t_m
+        workload = "deit_mrlal_tiny_patch16_224: the 12 mrlal_module calls of one training step (fwd+bwd), B=%d, 197x192 bf16" % B
+    else:
+        B = args.batch if args.batch != 256 else 384
+        shapes = [(16, 112, 1), (24, 56, 2), (40, 28, 2), (80, 14, 3), (112, 14, 3), (192, 7, 4), (320, 7, 1)]
+        for C, HW, nblk in shapes:
+            k = O.eca_kernel_size(C)
+            mk = lambda: torch.randn(B, C, HW, HW, device=dev, dtype=bf).contiguous(memory_format=torch.channels_last)
+            x, o_, dy = torch.relu(mk()).requires_grad_(), mk().requires_grad_(), mk()
+            Pm = [torch.randn(k, device=dev).requires_grad_(), torch.randn(k, device=dev).requires_grad_(),
+                  (torch.randn(C, 1, 3, 3, device=dev) * 0.3).requires_grad_(), torch.randn(C, 1, 1, device=dev).requires_grad_(),
+                  torch.ones(C, device=dev).requires_grad_(), torch.zeros(C, device=dev).requires_grad_()]
+            rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+            cfg = LightCfg(dim_perhead=8, k_size=k, bn_mode=_lib.BN_TRAIN, residual=True)
+            Pe = [p.detach().to(bf).requires_grad_() for p in Pm]
+
+            def mine():
+                light_tail(x, o_, *Pm, rm, rv, None, cfg=cfg).backward(dy)
+
+            def eager():
+                y, _, _ = O.light_tail(x, o_, Pe[0], Pe[1], Pe[2], Pe[3], C // 8, Pe[4], Pe[5], rm.to(bf), rv.to(bf))
+                y.backward(dy)
+
+            t_m, t_e = _time_fn(mine, 10, 3), _time_fn(eager, 5, 2)
+            nbytes = 8.0 * B * C * HW * HW * 2
+            rows[f"{C}x{HW}x{HW}"] = dict(ms=round(t_m, 4), eager_ms=round(t_e, 4), GBps=round(nbytes / t_m / 1e6, 1), blocks=nblk)
+            tot_bytes += nblk * nbytes
+            tot_ms += nblk * t_m
+            tot_eager += nblk * t_e
+        metric, unit, value = "efficientnet_b0_mrlal_tails_ms_per_step", "ms", tot_ms
+        workload = "EfficientNet-B0 block-output shapes @224 (SURVEY 8a A9), MRLA-light tail fwd+bwd per block, B=%d bf16 NHWC, d=8" % B
+    emit({"metric": metric, "value": round(value, 4), "unit": unit, "n_gpus": 1, "steps": 20, "warmup": 5,
+          "ms_per_step": round(value, 4), "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+          "data": "synthetic", "config": {"workload": workload, "l2": "tensors of the small shapes are L2-resident: latency-bound, "
+                                          "the HBM figure is for reference (SURVEY 8d)"},
+          "roofline": {"bound": "hbm", "achieved": round(tot_bytes / tot_ms / 1e6, 1), "peak": peak, "unit": "GB/s",
+                       "frac": round(tot_bytes / tot_ms / 1e6 / peak, 4), "traffic": None, "peak_kind": peak_kind,
+                       "per_shape": rows},
+          "gpu_eager_baseline": {"value": round(tot_eager, 4), "unit": "ms", "speedup": round(tot_eager / tot_ms, 2),
+                                 "what": "oracle restatement (the reference's ATen sequence) on the same GPU, same dtype"},
+          "gpu_launches": None})
 
 
 def main():
@@ -483,6 +623,13 @@ def main():
     ap.add_argument("--drop-path", type=float, default=0.2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--config", default="mrlal", choices=["mrlal", "mrlab", "deit_tail", "effnet_tail"],
+                    help="mrlal = BASELINE configs[1] (default); mrlab = configs[2]; deit_tail / effnet_tail = configs[4] / [3] "
+                         "at the module level")
+    ap.add_argument("--overlap-comm", action="store_true",
+                    help="N > 1: bucketed gradient all-reduce overlapped with backward instead of one all-reduce after it")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the same-GPU eager PyTorch baseline")
+    ap.add_argument("--compile-baseline", action="store_true", help="also time the eager baseline under torch.compile")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -494,7 +641,10 @@ def main():
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                    "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
             raise SystemExit(subprocess.call(cmd, stdout=_REAL_STDOUT))
-        run_product_arm(args)
+        if args.config in ("deit_tail", "effnet_tail"):
+            run_tail_config(args)
+        else:
+            run_product_arm(args)
 
 
 if __name__ == "__main__":

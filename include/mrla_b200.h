@@ -268,6 +268,43 @@ int mrla_maxpool3x3s2_forward(const void* x, void* y, unsigned char* idx, int B,
 int mrla_maxpool3x3s2_backward(const void* dy, const unsigned char* idx, void* dx, int B, int C, int H, int W, int dtype,
                                void* stream);
 
+
+/* Fused DeiT MRLA-light module (token layout), one kernel per direction, one CTA per sample (round 2):
+ *   xn = LayerNorm_x(x), on = LayerNorm_o(o)      deit/deit_mrla_light.py:195-196
+ *   out[:,0] = xn[:,0] ; out[:,1+t] = gate(img) * GELU(dwconv3x3(img))[t] + lambda * on[:,1+t], img = xn[:,1:] as [B,C,S,S]
+ *                                                deit/deit_mrla_light.py:157-180,199-207
+ * replacing both nn.LayerNorm calls, the cls split / torch.cat and the module's ATen sequence.  x, o, out, dout, dx, dox
+ * are dense [B, n = S*S+1, C] in `dtype`; C % 64 == 0, C*n*sizeof(dtype) must fit one CTA's shared memory
+ * (mrla_deit_light_supported()).  Parameters and gradients fp32. */
+typedef struct MrlaDeitArgs {
+  int32_t B, n, C, S;
+  int32_t dim_perhead, k_size, dtype, reserved0;
+  float eps;               /* LayerNorm eps (1e-6 in the reference) */
+  float reserved1;
+  const void* x;           /* [B,n,C] */
+  const void* o;           /* [B,n,C] */
+  void* out;               /* [B,n,C] */
+  const float* normx_w; const float* normx_b; const float* normo_w; const float* normo_b;   /* [C] */
+  const float* wq; const float* wk;   /* [k] */
+  const float* wv;         /* [C,9] */
+  const float* lam;        /* [C] */
+  float* stats_x;          /* [B,n,2] mean, rstd of LN_x   (saved by forward) */
+  float* stats_o;          /* [B,n,2] */
+  float* gate;             /* [B,C/d] */
+  const void* dout;        /* [B,n,C] (backward) */
+  void* dx;                /* [B,n,C] */
+  void* dox;               /* [B,n,C] */
+  float* dparams;          /* [14*C + 2*k]: dWv[C,9] | dlam | dnormx_w | dnormx_b | dnormo_w | dnormo_b [C each] | dwq[k] | dwk[k] */
+  float* scratch;          /* mrla_deit_light_scratch_bytes() : per-sample partials */
+  size_t scratch_bytes;
+} MrlaDeitArgs;
+
+size_t mrla_sizeof_deit_args(void);
+int mrla_deit_light_supported(const MrlaDeitArgs* a);          /* 1 if the fused kernels take this problem */
+size_t mrla_deit_light_scratch_bytes(const MrlaDeitArgs* a);
+int mrla_deit_light_forward(const MrlaDeitArgs* a, void* stream);
+int mrla_deit_light_backward(const MrlaDeitArgs* a, void* stream);
+
 /* Number of kernel launches the last forward / backward call on this thread enqueued
  * (bench.py reports it as gpu_launches). */
 int mrla_last_launch_count(void);

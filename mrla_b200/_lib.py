@@ -69,6 +69,17 @@ class MrlaBnArgs(ctypes.Structure):
     )
 
 
+class MrlaDeitArgs(ctypes.Structure):
+    """Mirror of `struct MrlaDeitArgs` (include/mrla_b200.h)."""
+    _fields_ = (
+        [(n, _i32) for n in ("B", "n", "C", "S", "dim_perhead", "k_size", "dtype", "reserved0")]
+        + [("eps", _f32), ("reserved1", _f32)]
+        + [(n, _vp) for n in ("x", "o", "out", "normx_w", "normx_b", "normo_w", "normo_b", "wq", "wk", "wv", "lam",
+                              "stats_x", "stats_o", "gate", "dout", "dx", "dox", "dparams", "scratch")]
+        + [("scratch_bytes", ctypes.c_size_t)]
+    )
+
+
 _lib = None
 _lock = threading.Lock()
 
@@ -77,6 +88,9 @@ EXPORTS = (
     "mrla_light_bwd_scratch_bytes", "mrla_light_bwd_fuses_relu", "mrla_light_fwd_folds_bn", "mrla_light_virtual_x", "mrla_light_forward", "mrla_light_backward",
     "mrla_nchw_to_nhwc", "mrla_add_relu", "mrla_sizeof_base_args", "mrla_base_bwd_scratch_bytes", "mrla_base_forward", "mrla_base_backward",
     "mrla_maxpool3x3s2_forward", "mrla_maxpool3x3s2_backward",
+    "mrla_sizeof_bn_args", "mrla_bn_scratch_bytes", "mrla_bn_forward", "mrla_bn_backward",
+    "mrla_sizeof_deit_args", "mrla_deit_light_supported", "mrla_deit_light_scratch_bytes", "mrla_deit_light_forward",
+    "mrla_deit_light_backward",
 )
 
 
@@ -131,6 +145,17 @@ def lib() -> ctypes.CDLL:
             f = getattr(L, f"mrla_bn_{d}")
             f.restype = ctypes.c_int
             f.argtypes = [ctypes.POINTER(MrlaBnArgs), ctypes.c_void_p]
+        L.mrla_sizeof_deit_args.restype = ctypes.c_size_t
+        if L.mrla_sizeof_deit_args() != ctypes.sizeof(MrlaDeitArgs):
+            raise RuntimeError("MrlaDeitArgs layout mismatch between _lib.py and include/mrla_b200.h")
+        L.mrla_deit_light_supported.restype = ctypes.c_int
+        L.mrla_deit_light_supported.argtypes = [ctypes.POINTER(MrlaDeitArgs)]
+        L.mrla_deit_light_scratch_bytes.restype = ctypes.c_size_t
+        L.mrla_deit_light_scratch_bytes.argtypes = [ctypes.POINTER(MrlaDeitArgs)]
+        for d in ("forward", "backward"):
+            f = getattr(L, f"mrla_deit_light_{d}")
+            f.restype = ctypes.c_int
+            f.argtypes = [ctypes.POINTER(MrlaDeitArgs), ctypes.c_void_p]
         for name, st in (("light", MrlaLightArgs), ("base", MrlaBaseArgs)):
             f = getattr(L, f"mrla_{name}_bwd_scratch_bytes")
             f.restype = ctypes.c_size_t

@@ -4,7 +4,7 @@
 // This is the same two-pass structure as the tail's moments / apply sweeps without the stencil:
 //   forward   k_bn_stats   R1     per-channel Σx, Σx² (per-CTA partials, fp64 finish)      -> mean, rstd, a, b
 //             k_bn_apply   R1 W1  y = act(a_c x + b_c)
-//   backward  k_bn_bwd_red R2     Σdz, Σdz·x   (dz = dy·[a x + b > 0] when ReLU is fused)  -> dγ dβ, A B C
+//   backward  k_bn_bwd_red R2     Σdz, Σdz·(x−μ) (dz = dy·[a x + b > 0] when ReLU is fused) -> dγ dβ, A B C
 //             k_bn_bwd_app R2 W1  dx = A_c dz + B_c x + C_c
 // View: x is [M = B·H·W rows, C channels] row-major (NHWC).  A thread owns 8 consecutive channels (one 128-bit
 // vector of bf16) and strides over rows; a 256-thread CTA is CL = C/8 channel lanes x RL row lanes.
@@ -40,8 +40,12 @@ __device__ __forceinline__ void bn_reduce_rows(const float (&v)[NV], float* sm, 
 }
 
 // ------------------------------------------------------------------------------------------- forward statistics
+// Sums are taken of (x - pivot_c), pivot_c = x[0, c]: E[x^2] - mean^2 on raw values cancels catastrophically when
+// |mean| >> std (mean 50, std 0.1 leaves no correct bits of the variance in fp32); shifted by any sample of the channel the
+// two terms are of the size of the variance itself.  pivot [C] is written by CTA 0 for k_bn_finalize.
 template <typename T>
-__global__ void __launch_bounds__(256) k_bn_stats(const T* __restrict__ x, float* __restrict__ part, BnShape s) {
+__global__ void __launch_bounds__(256) k_bn_stats(const T* __restrict__ x, float* __restrict__ part,
+                                                  float* __restrict__ pivot, BnShape s) {
   extern __shared__ float smem[];
   const int cl = threadIdx.x % s.CL, rl = threadIdx.x / s.CL;
   const bool active = rl < s.RL;
@@ -50,6 +54,12 @@ __global__ void __launch_bounds__(256) k_bn_stats(const T* __restrict__ x, float
 #pragma unroll
   for (int i = 0; i < 2 * kSV; ++i) acc[i] = 0.f;
   if (active) {
+    float pv[kSV];
+    Vec8<T>::ld(x + c, pv);
+    if (blockIdx.x == 0 && rl == 0) {
+#pragma unroll
+      for (int i = 0; i < kSV; ++i) pivot[c + i] = pv[i];
+    }
     const int64_t stride = (int64_t)gridDim.x * s.RL;
     int64_t row = (int64_t)blockIdx.x * s.RL + rl;
     for (; row + stride < s.M; row += 2 * stride) {   // two independent 128-bit loads in flight
@@ -58,8 +68,9 @@ __global__ void __launch_bounds__(256) k_bn_stats(const T* __restrict__ x, float
       Vec8<T>::ld(x + (row + stride) * s.C + c, b);
 #pragma unroll
       for (int i = 0; i < kSV; ++i) {
-        acc[i] += a[i] + b[i];
-        acc[kSV + i] = fmaf(a[i], a[i], fmaf(b[i], b[i], acc[kSV + i]));
+        const float da = a[i] - pv[i], db = b[i] - pv[i];
+        acc[i] += da + db;
+        acc[kSV + i] = fmaf(da, da, fmaf(db, db, acc[kSV + i]));
       }
     }
     if (row < s.M) {
@@ -67,8 +78,9 @@ __global__ void __launch_bounds__(256) k_bn_stats(const T* __restrict__ x, float
       Vec8<T>::ld(x + row * s.C + c, a);
 #pragma unroll
       for (int i = 0; i < kSV; ++i) {
-        acc[i] += a[i];
-        acc[kSV + i] = fmaf(a[i], a[i], acc[kSV + i]);
+        const float da = a[i] - pv[i];
+        acc[i] += da;
+        acc[kSV + i] = fmaf(da, da, acc[kSV + i]);
       }
     }
   }
@@ -76,7 +88,8 @@ __global__ void __launch_bounds__(256) k_bn_stats(const T* __restrict__ x, float
 }
 
 // part [nparts, 2, C] -> mean, rstd (saved) ; coef [2,C]: a = γ r, b = β − γ r μ ; running stats
-static __global__ void __launch_bounds__(1024) k_bn_finalize(const float* __restrict__ part, int nparts, int C, double n,
+static __global__ void __launch_bounds__(1024) k_bn_finalize(const float* __restrict__ part, const float* __restrict__ pivot,
+                                                            int nparts, int C, double n,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float* __restrict__ running_mean, float* __restrict__ running_var,
                                                             float* __restrict__ stats, float* __restrict__ coef, float eps,
@@ -99,8 +112,9 @@ static __global__ void __launch_bounds__(1024) k_bn_finalize(const float* __rest
   if (training) {
     double a1 = 0.0, a2 = 0.0;
     for (int j = 0; j < 32; ++j) { a1 += r1[j][cl]; a2 += r2[j][cl]; }
-    mu = a1 / n;
-    double var = a2 / n - mu * mu;
+    const double ms = a1 / n;            // mean of the shifted values
+    mu = (double)pivot[c] + ms;
+    double var = a2 / n - ms * ms;
     if (var < 0.0) var = 0.0;
     r = 1.0 / sqrt(var + (double)eps);
     if (update_running && running_mean != nullptr) {
@@ -146,15 +160,18 @@ __global__ void __launch_bounds__(256) k_bn_apply(const T* __restrict__ x, T* __
 // ------------------------------------------------------------------------------------------- backward reduce
 template <typename T, bool RELU>
 __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const T* __restrict__ dy, const T* __restrict__ x,
-                                                       const float* __restrict__ coef, float* __restrict__ part,
-                                                       BnShape s) {
+                                                       const float* __restrict__ coef, const float* __restrict__ stats,
+                                                       float* __restrict__ part, BnShape s) {
   extern __shared__ float smem[];
   const int cl = threadIdx.x % s.CL, rl = threadIdx.x / s.CL;
   const bool active = rl < s.RL;
   const int c = cl * kSV;
-  float a[kSV], b[kSV];
+  float a[kSV], b[kSV], mu[kSV];
 #pragma unroll
-  for (int i = 0; i < kSV; ++i) { a[i] = active ? coef[c + i] : 0.f; b[i] = active ? coef[s.C + c + i] : 0.f; }
+  for (int i = 0; i < kSV; ++i) {
+    a[i] = active ? coef[c + i] : 0.f; b[i] = active ? coef[s.C + c + i] : 0.f;
+    mu[i] = active ? stats[c + i] : 0.f;
+  }
   float acc[2 * kSV];
 #pragma unroll
   for (int i = 0; i < 2 * kSV; ++i) acc[i] = 0.f;
@@ -169,7 +186,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const T* __restrict__ dy,
       for (int i = 0; i < kSV; ++i) {
         const float dz = (RELU && fmaf(a[i], v[i], b[i]) <= 0.f) ? 0.f : g[i];
         acc[i] += dz;
-        acc[kSV + i] = fmaf(dz, v[i], acc[kSV + i]);
+        acc[kSV + i] = fmaf(dz, v[i] - mu[i], acc[kSV + i]);   // centred: no sum dz*x - mean*sum dz cancellation
       }
     }
   }
@@ -182,7 +199,7 @@ static __global__ void __launch_bounds__(1024) k_bn_bwd_finalize(const float* __
                                                                 double n, const float* __restrict__ gamma,
                                                                 const float* __restrict__ stats,
                                                                 float* __restrict__ bcoef, float* __restrict__ dgamma,
-                                                                float* __restrict__ dbeta, int training) {
+                                                                float* __restrict__ dbeta, int training, int centred) {
   __shared__ double r1[32][33], r2[32][33];
   const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
@@ -200,7 +217,8 @@ static __global__ void __launch_bounds__(1024) k_bn_bwd_finalize(const float* __
   double a1 = 0.0, a2 = 0.0;
   for (int j = 0; j < 32; ++j) { a1 += r1[j][cl]; a2 += r2[j][cl]; }
   const double mu = stats[c], r = stats[C + c], ga = gamma ? (double)gamma[c] : 1.0;
-  const double dbe = a1, dga = r * (a2 - mu * a1);   // Σdz x̂
+  // Σdz x̂ : the second sum is Σdz (x - mean) (centred, k_bn_bwd_reduce) or Σdz x (raw, from the MRLA tail's sweep B)
+  const double dbe = a1, dga = centred ? r * a2 : r * (a2 - mu * a1);
   if (dbeta) dbeta[c] = (float)dbe;
   if (dgamma) dgamma[c] = (float)dga;
   const double m1 = training ? dbe / n : 0.0, m2 = training ? dga / n : 0.0;

@@ -26,11 +26,12 @@ template <typename T>
 static int bn_forward_t(const MrlaBnArgs& a, const BnShape& s, cudaStream_t st) {
   const T* x = static_cast<const T*>(a.x);
   T* y = static_cast<T*>(a.y);
+  float* pivot = a.scratch + (size_t)s.nparts * 2 * a.C + (size_t)3 * a.C;   // [C] shift of the statistics sums
   if (a.training) {
-    k_bn_stats<T><<<s.nparts, 256, 256 * 2 * kSV * sizeof(float), st>>>(x, a.scratch, s);
+    k_bn_stats<T><<<s.nparts, 256, 256 * 2 * kSV * sizeof(float), st>>>(x, a.scratch, pivot, s);
     MRLA_CHECK_LAUNCH();
   }
-  k_bn_finalize<<<(a.C + 31) / 32, 1024, 0, st>>>(a.scratch, s.nparts, a.C, (double)a.M, a.gamma, a.beta, a.running_mean,
+  k_bn_finalize<<<(a.C + 31) / 32, 1024, 0, st>>>(a.scratch, pivot, s.nparts, a.C, (double)a.M, a.gamma, a.beta, a.running_mean,
                                                  a.running_var, a.stats, a.coef, a.eps, a.momentum, a.training,
                                                  a.update_running);
   MRLA_CHECK_LAUNCH();
@@ -49,13 +50,13 @@ static int bn_backward_t(const MrlaBnArgs& a, const BnShape& s, cudaStream_t st)
   float* bcoef = a.scratch + (size_t)s.nparts * 2 * a.C;
   const size_t sm = 256 * 2 * kSV * sizeof(float);
   if (a.sums == nullptr) {
-    if (a.relu) k_bn_bwd_reduce<T, true><<<s.nparts, 256, sm, st>>>(dy, x, a.coef, a.scratch, s);
-    else k_bn_bwd_reduce<T, false><<<s.nparts, 256, sm, st>>>(dy, x, a.coef, a.scratch, s);
+    if (a.relu) k_bn_bwd_reduce<T, true><<<s.nparts, 256, sm, st>>>(dy, x, a.coef, a.stats, a.scratch, s);
+    else k_bn_bwd_reduce<T, false><<<s.nparts, 256, sm, st>>>(dy, x, a.coef, a.stats, a.scratch, s);
     MRLA_CHECK_LAUNCH();
   }
   // a.sums: the producer of dy (sweep B of the MRLA tail, MrlaLightArgs.dz_sums) already reduced sum dy, sum dy*x
   k_bn_bwd_finalize<<<(a.C + 31) / 32, 1024, 0, st>>>(a.sums ? a.sums : a.scratch, a.sums ? 1 : s.nparts, a.C, (double)a.M,
-                                                     a.gamma, a.stats, bcoef, a.dgamma, a.dbeta, a.training);
+                                                     a.gamma, a.stats, bcoef, a.dgamma, a.dbeta, a.training, a.sums ? 0 : 1);
   MRLA_CHECK_LAUNCH();
   if (a.relu) k_bn_bwd_apply<T, true><<<s.nparts, 256, 0, st>>>(dy, x, dx, a.coef, bcoef, s);
   else k_bn_bwd_apply<T, false><<<s.nparts, 256, 0, st>>>(dy, x, dx, a.coef, bcoef, s);
@@ -73,10 +74,11 @@ size_t mrla_sizeof_bn_args(void) { return sizeof(MrlaBnArgs); }
 size_t mrla_bn_scratch_bytes(const MrlaBnArgs* a) {
   BnShape s;
   if (bn_plan(a, &s)) return 0;
-  return ((size_t)s.nparts * 2 * a->C + (size_t)3 * a->C) * sizeof(float);
+  return ((size_t)s.nparts * 2 * a->C + (size_t)4 * a->C) * sizeof(float);   // partials | bcoef [3,C] | pivot [C]
 }
 
 int mrla_bn_forward(const MrlaBnArgs* a, void* stream) {
+  NvtxRange nvtx_("mrla_bn_forward");
   g_launch_count = 0;
   BnShape s;
   int rc = bn_plan(a, &s);
@@ -95,6 +97,7 @@ int mrla_bn_forward(const MrlaBnArgs* a, void* stream) {
 }
 
 int mrla_bn_backward(const MrlaBnArgs* a, void* stream) {
+  NvtxRange nvtx_("mrla_bn_backward");
   g_launch_count = 0;
   BnShape s;
   int rc = bn_plan(a, &s);

@@ -4,8 +4,18 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <nvtx3/nvToolsExt.h>
 
 namespace mrla {
+
+// NVTX range around a C-ABI entry point (SURVEY.md section 5 "tracing"): nsys / ncu timelines show one named range per
+// call of the library with the kernels it enqueued inside.  Header-only NVTX v3: a no-op when no tool is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // ------------------------------------------------------------------ dtype conversion
 template <typename T> __device__ __forceinline__ float to_f(T v);

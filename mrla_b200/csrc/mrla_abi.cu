@@ -111,6 +111,7 @@ int mrla_light_virtual_x(const MrlaLightArgs* a) {
 }
 
 int mrla_light_forward(const MrlaLightArgs* a, void* stream) {
+  NvtxRange nvtx_("mrla_light_forward");
   g_launch_count = 0;
   int rc = check_common(a, false);
   if (rc) return rc;
@@ -124,6 +125,7 @@ int mrla_light_forward(const MrlaLightArgs* a, void* stream) {
 }
 
 int mrla_light_backward(const MrlaLightArgs* a, void* stream) {
+  NvtxRange nvtx_("mrla_light_backward");
   g_launch_count = 0;
   int rc = check_common(a, true);
   if (rc) return rc;
@@ -139,6 +141,7 @@ int mrla_light_backward(const MrlaLightArgs* a, void* stream) {
 
 int mrla_nchw_to_nhwc(const void* src, void* dst, int B, int C, int HW, int dtype, int64_t bs_src, int64_t bs_dst,
                       void* stream) {
+  NvtxRange nvtx_("mrla_nchw_to_nhwc");
   g_launch_count = 0;
   if (!src || !dst) return MRLA_ERR_NULL;
   if (B < 1 || C < 1 || HW < 1 || B > 65535) return MRLA_ERR_SHAPE;
@@ -155,6 +158,7 @@ int mrla_nchw_to_nhwc(const void* src, void* dst, int B, int C, int HW, int dtyp
 }
 
 int mrla_add_relu(const void* z, const void* idt, void* x, int64_t n, int dtype, void* stream) {
+  NvtxRange nvtx_("mrla_add_relu");
   g_launch_count = 0;
   if (!z || !idt || !x) return MRLA_ERR_NULL;
   if (n < 1) return MRLA_ERR_SHAPE;
@@ -183,6 +187,7 @@ size_t mrla_base_bwd_scratch_bytes(const MrlaBaseArgs* a) {
 }
 
 int mrla_base_forward(const MrlaBaseArgs* a, void* stream) {
+  NvtxRange nvtx_("mrla_base_forward");
   g_launch_count = 0;
   int rc = check_base(a, false);
   if (rc) return rc;
@@ -196,6 +201,7 @@ int mrla_base_forward(const MrlaBaseArgs* a, void* stream) {
 }
 
 int mrla_base_backward(const MrlaBaseArgs* a, void* stream) {
+  NvtxRange nvtx_("mrla_base_backward");
   g_launch_count = 0;
   int rc = check_base(a, true);
   if (rc) return rc;

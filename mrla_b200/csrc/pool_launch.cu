@@ -112,6 +112,7 @@ extern "C" {
 
 int mrla_maxpool3x3s2_forward(const void* x, void* y, unsigned char* idx, int B, int C, int H, int W, int dtype,
                               void* stream) {
+  NvtxRange nvtx_("mrla_maxpool3x3s2_forward");
   g_launch_count = 0;
   PoolShape s;
   int rc = pool_shape(B, C, H, W, dtype, &s);
@@ -136,6 +137,7 @@ int mrla_maxpool3x3s2_forward(const void* x, void* y, unsigned char* idx, int B,
 
 int mrla_maxpool3x3s2_backward(const void* dy, const unsigned char* idx, void* dx, int B, int C, int H, int W, int dtype,
                                void* stream) {
+  NvtxRange nvtx_("mrla_maxpool3x3s2_backward");
   g_launch_count = 0;
   PoolShape s;
   int rc = pool_shape(B, C, H, W, dtype, &s);

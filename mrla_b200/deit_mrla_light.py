@@ -2,7 +2,8 @@
 `mrlal_layer` (:117-180, GELU on V), `mrlal_module` (:183-209: LayerNorm of x and o, cls-token pass-through, lambda
 recurrence on the 14x14 token image) with identical class names, constructor arguments and parameter names.
 The token image [B, n-1, C] is read in place as an NHWC activation with batch stride n*C (no permute / copy);
-the two LayerNorms stay on PyTorch's library kernel in this round (fusing them into sweep 1 is listed in DESIGN.md)."""
+round 2: the whole module (both LayerNorms, cls pass-through, gate, GELU-V, lambda) is ONE kernel per direction
+(csrc/deit_fused.cuh, one CTA per sample) wherever a sample fits a CTA's shared memory; other shapes keep the round-1 path."""
 from __future__ import annotations
 
 import math
@@ -14,7 +15,7 @@ import torch.nn.functional as F
 
 from . import _lib
 from .modules.mrla_light_module import mrla_light_layer
-from .ops import light_tail
+from .ops import deit_light_module, deit_light_supported, light_tail
 
 __all__ = ["mrlal_layer", "mrlal_module", "tokens_as_image"]
 
@@ -53,6 +54,17 @@ class mrlal_module(nn.Module):
         self.normo = norm_layer(input_dim)
 
     def forward(self, xt, ot_1):
+        m = self.mrla
+        plain_ln = all(type(ln) is nn.LayerNorm and ln.elementwise_affine and ln.bias is not None
+                       and tuple(ln.normalized_shape) == (xt.shape[-1],) for ln in (self.normx, self.normo))
+        if (plain_ln and self.normx.eps == self.normo.eps and ot_1.shape == xt.shape and ot_1.dtype == xt.dtype
+                and xt.is_contiguous() and ot_1.is_contiguous() and deit_light_supported(xt, self.dim_perhead, m.k_size)):
+            # one kernel per direction: LN_x, LN_o, cls pass-through, gate, GELU-V, lambda (csrc/deit_fused.cuh)
+            return deit_light_module(xt, ot_1, self.normx.weight, self.normx.bias, self.normo.weight, self.normo.bias,
+                                     m.Wq.weight, m.Wk.weight, m.Wv.weight, self.lambda_t, dim_perhead=self.dim_perhead,
+                                     k_size=m.k_size, eps=self.normx.eps)
+        # other norm layers / shapes the fused kernel does not take (C % 64 != 0, a sample larger than one CTA's shared
+        # memory): LayerNorms through the library, MRLA through the generic tail kernels
         xn = self.normx(xt)
         on = self.normo(ot_1)
         m = self.mrla

@@ -14,9 +14,11 @@ mmdet backbone, DeiT) is the same op with different flags.
 from __future__ import annotations
 
 import ctypes
+import functools
 from typing import NamedTuple, Optional
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 
@@ -108,6 +110,20 @@ def _on(t: torch.Tensor):
     return torch.cuda.device(t.device)
 
 
+def _guard(fn):
+    """Run an autograd.Function forward / backward on the device (and its current stream) of the first CUDA tensor
+    argument — everything inside (`_stream()`, scratch `torch.empty(device=...)`, tensor-map encoding, launches) then
+    agrees with where the data lives."""
+    @functools.wraps(fn)
+    def wrapper(ctx, *args, **kw):
+        t = next((a for a in args if isinstance(a, torch.Tensor) and a.is_cuda), None)
+        if t is None or t.device.index == torch.cuda.current_device():
+            return fn(ctx, *args, **kw)
+        with torch.cuda.device(t.device):
+            return fn(ctx, *args, **kw)
+    return wrapper
+
+
 def _require_cuda(t: torch.Tensor, name: str):
     if not t.is_cuda:
         raise RuntimeError(f"mrla_b200: `{name}` must be a CUDA tensor — the MRLA kernels are sm_100a only "
@@ -157,8 +173,9 @@ def _to_nhwc(t: torch.Tensor) -> torch.Tensor:
     B, C, H, W = t.shape
     out = torch.empty((B, H, W, C), dtype=t.dtype, device=t.device).permute(0, 3, 1, 2)
     L = _lib.lib()
-    _lib.check(L.mrla_nchw_to_nhwc(t.data_ptr(), out.data_ptr(), B, C, H * W, _DTYPES[t.dtype], t.stride(0),
-                                   C * H * W, _stream()), "mrla_nchw_to_nhwc")
+    with _on(t):
+        _lib.check(L.mrla_nchw_to_nhwc(t.data_ptr(), out.data_ptr(), B, C, H * W, _DTYPES[t.dtype], t.stride(0),
+                                       C * H * W, _stream()), "mrla_nchw_to_nhwc")
     return out
 
 
@@ -166,10 +183,13 @@ class _ToNHWC(torch.autograd.Function):
     """Differentiable wrapper: the gradient simply flows back in whatever layout it arrives."""
 
     @staticmethod
+    @_guard
     def forward(ctx, t):
         return _to_nhwc(t)
 
     @staticmethod
+    @once_differentiable
+    @_guard
     def backward(ctx, g):
         return g
 
@@ -182,6 +202,7 @@ def _want_nhwc(x: torch.Tensor) -> bool:
 # --------------------------------------------------------------------------------- the fused op
 class _LightTail(torch.autograd.Function):
     @staticmethod
+    @_guard
     def forward(ctx, x, o, wq, wk, wv, lam, gamma, beta, running_mean, running_var, drop_scale, cfg: LightCfg, out,
                 z_coef=None, z_coef_fn=None):
         # z_coef / z_coef_fn are only used by _Bn3LightTail (which calls this method with its own context object):
@@ -289,6 +310,8 @@ class _LightTail(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
+    @_guard
     def backward(ctx, dy):
         L = _lib.lib()
         x_c, o_c, wq32, wk32, wv32, lam32, ga32, ds32, mom, gate, stats, z_coef = ctx.saved_tensors
@@ -389,6 +412,7 @@ class _Bn3LightTail(torch.autograd.Function):
     folds (bn3_tail_eligible); every other case keeps bn3 as its own op (ops.bn_act) in front of light_tail."""
 
     @staticmethod
+    @_guard
     def forward(ctx, c3, o, w3, b3, rm3, rv3, bn3_args, wq, wk, wv, lam, gamma, beta, running_mean, running_var,
                 drop_scale, cfg: LightCfg):
         L = _lib.lib()
@@ -432,6 +456,8 @@ class _Bn3LightTail(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
+    @_guard
     def backward(ctx, dy):
         L = _lib.lib()
         saved = ctx.saved_tensors
@@ -467,6 +493,8 @@ def bn3_tail_eligible(c3: torch.Tensor, o: torch.Tensor, bn3: "torch.nn.BatchNor
     mrla_light_fwd_folds_bn with the layout / strides / alignment the op would use.)"""
     if not (cfg.fuse_add_relu and cfg.bn_mode == _lib.BN_TRAIN and cfg.act == _lib.ACT_NONE):
         return False
+    if not is_plain_batchnorm(bn3):
+        return False
     if not (bn3.training or bn3.running_mean is None) or bn3.weight is None or bn3.bias is None:
         return False
     if bn3.running_mean is not None and bn3.running_mean.dtype != torch.float32:
@@ -493,7 +521,7 @@ def bn3_light_tail(c3: torch.Tensor, o: torch.Tensor, bn3: "torch.nn.BatchNorm2d
     update = bn3.training and bn3.track_running_stats and bn3.running_mean is not None
     if update:
         bn3.num_batches_tracked += 1
-        momentum = bn3.momentum if bn3.momentum is not None else 1.0 / float(int(bn3.num_batches_tracked))
+        momentum = effective_momentum(bn3)
     else:
         momentum = 0.0
     return _Bn3LightTail.apply(c3, o, bn3.weight, bn3.bias, bn3.running_mean, bn3.running_var,
@@ -512,6 +540,86 @@ def light_tail(x: torch.Tensor, o: Optional[torch.Tensor], wq, wk, wv, lam=None,
     the sweep-1 variant the model runs)."""
     return _LightTail.apply(x, o, wq, wk, wv, lam, gamma, beta, running_mean, running_var, drop_scale, cfg, out,
                             z_coef, None)
+
+
+# ===================================================================================== DeiT fused module
+class _DeitLightModule(torch.autograd.Function):
+    """deit/deit_mrla_light.py:194-209 (`mrlal_module.forward`) as ONE kernel per direction: both LayerNorms, cls
+    pass-through, GAP + ECA gate, depthwise conv + GELU, lambda recurrence (csrc/deit_fused.cuh)."""
+
+    @staticmethod
+    def forward(ctx, x, o, nx_w, nx_b, no_w, no_b, wq, wk, wv, lam, dim_perhead, k_size, eps):
+        L = _lib.lib()
+        B, n, C = x.shape
+        S = int(round((n - 1) ** 0.5))
+        out = torch.empty_like(x)
+        f32 = dict(dtype=torch.float32, device=x.device)
+        stats = torch.empty((2, B, n, 2), **f32)
+        gate = torch.empty((B, C // dim_perhead), **f32)
+        P = [_f32(t) for t in (nx_w, nx_b, no_w, no_b, wq, wk, wv, lam)]
+        a = _lib.MrlaDeitArgs()
+        a.B, a.n, a.C, a.S = B, n, C, S
+        a.dim_perhead, a.k_size, a.dtype, a.eps = dim_perhead, k_size, _DTYPES[x.dtype], eps
+        a.x, a.o, a.out = _ptr(x), _ptr(o), _ptr(out)
+        (a.normx_w, a.normx_b, a.normo_w, a.normo_b, a.wq, a.wk, a.wv, a.lam) = [_ptr(t) for t in P]
+        a.stats_x, a.stats_o, a.gate = _ptr(stats[0]), _ptr(stats[1]), _ptr(gate)
+        _lib.check(L.mrla_deit_light_forward(ctypes.byref(a), _stream()), "mrla_deit_light_forward")
+        launch_counter["fwd"] += L.mrla_last_launch_count()
+        ctx.meta = (dim_perhead, k_size, eps)
+        ctx.param_meta = [(p.shape, p.dtype, p.stride()) for p in (nx_w, nx_b, no_w, no_b, wq, wk, wv, lam)]
+        ctx.save_for_backward(x, o, stats, gate, *P)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    @_guard
+    def backward(ctx, dout):
+        L = _lib.lib()
+        x, o, stats, gate, *P = ctx.saved_tensors
+        dim_perhead, k_size, eps = ctx.meta
+        B, n, C = x.shape
+        dout = dout.contiguous()
+        if dout.dtype != x.dtype:
+            dout = dout.to(x.dtype)
+        dx, do = torch.empty_like(x), torch.empty_like(o)
+        f32 = dict(dtype=torch.float32, device=x.device)
+        dpar = torch.empty(14 * C + 2 * k_size, **f32)
+        a = _lib.MrlaDeitArgs()
+        a.B, a.n, a.C, a.S = B, n, C, int(round((n - 1) ** 0.5))
+        a.dim_perhead, a.k_size, a.dtype, a.eps = dim_perhead, k_size, _DTYPES[x.dtype], eps
+        a.x, a.o = _ptr(x), _ptr(o)
+        (a.normx_w, a.normx_b, a.normo_w, a.normo_b, a.wq, a.wk, a.wv, a.lam) = [_ptr(t) for t in P]
+        a.stats_x, a.stats_o, a.gate = _ptr(stats[0]), _ptr(stats[1]), _ptr(gate)
+        a.dout, a.dx, a.dox, a.dparams = _ptr(dout), _ptr(dx), _ptr(do), _ptr(dpar)
+        nbytes = L.mrla_deit_light_scratch_bytes(ctypes.byref(a))
+        scratch = torch.empty((max(nbytes, 4) + 3) // 4, **f32)
+        a.scratch, a.scratch_bytes = _ptr(scratch), scratch.numel() * 4
+        _lib.check(L.mrla_deit_light_backward(ctypes.byref(a), _stream()), "mrla_deit_light_backward")
+        launch_counter["bwd"] += L.mrla_last_launch_count()
+        k = k_size
+        seg = [dpar[9 * C + 1 * C:9 * C + 2 * C], dpar[9 * C + 2 * C:9 * C + 3 * C], dpar[9 * C + 3 * C:9 * C + 4 * C],
+               dpar[9 * C + 4 * C:9 * C + 5 * C], dpar[14 * C:14 * C + k], dpar[14 * C + k:14 * C + 2 * k], dpar[:9 * C],
+               dpar[9 * C:10 * C]]   # order of the forward arguments: nx_w nx_b no_w no_b wq wk wv lam
+        grads = [_like_param(g_, m_) for g_, m_ in zip(seg, ctx.param_meta)]
+        return (dx, do, *grads, None, None, None)
+
+
+def deit_light_supported(x: torch.Tensor, dim_perhead: int, k_size: int) -> bool:
+    """Does the fused DeiT kernel take this token tensor ([B, S*S+1, C] dense, C % 64 == 0, one sample fits a CTA)?"""
+    if not (x.is_cuda and x.dim() == 3 and x.is_contiguous() and x.dtype in _DTYPES):
+        return False
+    B, n, C = x.shape
+    S = int(round((n - 1) ** 0.5))
+    if S * S + 1 != n:
+        return False
+    a = _lib.MrlaDeitArgs()
+    a.B, a.n, a.C, a.S = B, n, C, S
+    a.dim_perhead, a.k_size, a.dtype = dim_perhead, k_size, _DTYPES[x.dtype]
+    return bool(_lib.lib().mrla_deit_light_supported(ctypes.byref(a)))
+
+
+def deit_light_module(x, o, nx_w, nx_b, no_w, no_b, wq, wk, wv, lam, *, dim_perhead: int, k_size: int, eps: float):
+    return _DeitLightModule.apply(x, o, nx_w, nx_b, no_w, no_b, wq, wk, wv, lam, dim_perhead, k_size, eps)
 
 
 # ===================================================================================== MRLA-base
@@ -583,6 +691,7 @@ class StageCache:
 
 class _BaseTail(torch.autograd.Function):
     @staticmethod
+    @_guard
     def forward(ctx, x, wq, wk, wv, gamma, beta, ext_k, ext_v, token, running_mean, running_var, drop_scale, cache,
                 t, cfg: BaseCfg, out):
         _require_cuda(x, "x")
@@ -641,6 +750,8 @@ class _BaseTail(torch.autograd.Function):
         return y, torch.zeros((), dtype=torch.float32, device=x.device)
 
     @staticmethod
+    @once_differentiable
+    @_guard
     def backward(ctx, dy, _dtoken):
         L = _lib.lib()
         x_c, s, wq32, wk32, wv32, ga32, ds32, sxq, p, chan = ctx.saved_tensors
@@ -684,7 +795,9 @@ class _BaseTail(torch.autograd.Function):
         _lib.check(L.mrla_base_backward(ctypes.byref(a), _stream()), "mrla_base_backward")
         _Prof.end("base_bwd", (B, C, H, W, x_c.dtype, layout), ev)
         launch_counter["bwd"] += L.mrla_last_launch_count()
-        cache.bwd_started = True
+        # the blocks of a stage run their backward last-to-first; once the block that opened the cache (t = n_ext + 1) is
+        # through, a later backward over the same graph (retain_graph=True) starts from overwritten, not stale, dV / dK
+        cache.bwd_started = t > cache.n_ext + 1
         def back(i, g_):
             meta = ctx.param_meta[i]
             return None if meta is None or g_ is None else _like_param(g_, meta)
@@ -745,6 +858,25 @@ def base_tail(x, prev_k, prev_v, wq, wk, wv, gamma=None, beta=None, running_mean
 
 
 # ===================================================================================== BatchNorm (+ReLU) producer
+def is_plain_batchnorm(bn) -> bool:
+    """The fused paths implement nn.BatchNorm2d and nothing else.  `norm_layer=nn.SyncBatchNorm` /
+    `convert_sync_batchnorm` (statistics all-reduced across ranks), GroupNorm, FrozenBatchNorm or a user subclass with
+    its own forward must keep their own semantics: callers route them through the module itself."""
+    return type(bn) is torch.nn.BatchNorm2d
+
+
+def effective_momentum(bn, pending: int = 0) -> float:
+    """nn.BatchNorm2d momentum for this step (momentum=None: cumulative moving average 1/num_batches_tracked, counting
+    this step: `pending` = 1 if the caller increments the counter only after the op).  The counter lives on the device, so momentum=None costs a host sync per call and
+    cannot be captured in a CUDA graph."""
+    if bn.momentum is not None:
+        return bn.momentum
+    if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+        raise RuntimeError("mrla_b200: BatchNorm2d(momentum=None) reads num_batches_tracked on the host every step and "
+                           "cannot be captured in a CUDA graph; give the module a numeric momentum")
+    return 1.0 / float(int(bn.num_batches_tracked) + pending)
+
+
 def bn_act_eligible(x: torch.Tensor) -> bool:
     """Channels-last dense [B,C,H,W] (or [M,C]) CUDA activation the NHWC BatchNorm kernels can take."""
     if not x.is_cuda or x.dtype not in _DTYPES:
@@ -761,6 +893,7 @@ def bn_act_eligible(x: torch.Tensor) -> bool:
 
 class _BnAct(torch.autograd.Function):
     @staticmethod
+    @_guard
     def forward(ctx, x, weight, bias, running_mean, running_var, training, update_running, momentum, eps, relu):
         L = _lib.lib()
         if x.dim() == 4:
@@ -792,6 +925,8 @@ class _BnAct(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
+    @_guard
     def backward(ctx, dy):
         L = _lib.lib()
         x, w32, stats, coef = ctx.saved_tensors
@@ -830,6 +965,9 @@ def bn_act(x, bn: "torch.nn.BatchNorm2d", relu: bool = False) -> torch.Tensor:
     """BatchNorm2d (+ReLU) of the bottleneck on the fused NHWC kernels, with nn.BatchNorm2d semantics (train / eval,
     running statistics, momentum=None cumulative average, affine or not).  Activations that are not channels-last
     (or have C % 8 != 0) go through the library's own batch_norm (+relu) — they are not on the MRLA path."""
+    if not is_plain_batchnorm(bn):
+        y = bn(x)   # SyncBatchNorm / GroupNorm / frozen variants: the module's own semantics
+        return torch.relu(y) if relu else y
     use_batch = bn.training or bn.running_mean is None
     if not bn_act_eligible(x) or (not use_batch and bn.running_mean is None):
         y = bn(x)
@@ -837,7 +975,7 @@ def bn_act(x, bn: "torch.nn.BatchNorm2d", relu: bool = False) -> torch.Tensor:
     update = bn.training and bn.track_running_stats and bn.running_mean is not None
     if update:
         bn.num_batches_tracked += 1
-        momentum = bn.momentum if bn.momentum is not None else 1.0 / float(int(bn.num_batches_tracked))
+        momentum = effective_momentum(bn)
     else:
         momentum = 0.0
     rm, rv = bn.running_mean, bn.running_var
@@ -860,6 +998,7 @@ def _max_pool_eligible(x: torch.Tensor) -> bool:
 
 class _MaxPool3x3s2(torch.autograd.Function):
     @staticmethod
+    @_guard
     def forward(ctx, x):
         L = _lib.lib()
         B, C, H, W = x.shape
@@ -874,6 +1013,8 @@ class _MaxPool3x3s2(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
+    @_guard
     def backward(ctx, dy):
         L = _lib.lib()
         (idx,) = ctx.saved_tensors

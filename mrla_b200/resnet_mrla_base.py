@@ -11,7 +11,7 @@ import torch.nn.functional as F
 from . import _lib
 from .drop import DropPath
 from .modules.mrla_base_module import mrla_base_layer
-from .ops import bn_act, max_pool
+from .ops import bn_act, is_plain_batchnorm, max_pool
 from .resnet_mrla_light import _bn_effective_momentum, _conv1x1, _conv3x3
 
 __all__ = ["ResNet_mrlab", "MRLA_Bottleneck", "mrla_module", "mrla_base_block_tail", "resnet50_mrlab",
@@ -41,6 +41,11 @@ def mrla_base_block_tail(out, prev_k, prev_v, mrla: mrla_module, bn: nn.BatchNor
     layer = mrla.mrla
     if mrla.init_cell:
         prev_k = prev_v = None
+    if not is_plain_batchnorm(bn):
+        # SyncBatchNorm / GroupNorm / ...: the norm module keeps its own semantics (reference :124-127 unfused)
+        s, k, v = mrla(out, prev_k, prev_v)
+        z = bn(s)
+        return out + drop_path(torch.relu(z) if relu else z), k, v
     use_batch_stats = bn.training or bn.running_mean is None
     if use_batch_stats:
         mode = _lib.BN_TRAIN

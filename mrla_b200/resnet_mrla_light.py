@@ -16,7 +16,8 @@ import torch.nn.functional as F
 from . import _lib
 from .drop import DropPath
 from .modules.mrla_light_module import mrla_light_layer
-from .ops import bn3_light_tail, bn3_tail_eligible, bn_act, light_tail, max_pool
+from .ops import (bn3_light_tail, bn3_tail_eligible, bn_act, effective_momentum, is_plain_batchnorm, light_tail,
+                  max_pool)
 
 __all__ = ["ResNet_mrlal", "MRLA_Bottleneck", "mrla_module", "mrla_light_block_tail",
            "resnet50_mrlal", "resnet101_mrlal"]
@@ -37,9 +38,8 @@ class mrla_module(nn.Module):
 
 
 def _bn_effective_momentum(bn: nn.BatchNorm2d) -> float:
-    if bn.momentum is None:  # cumulative moving average
-        return 1.0 / float(int(bn.num_batches_tracked) + 1)
-    return bn.momentum
+    # momentum=None: cumulative moving average; the counter is incremented after the op
+    return effective_momentum(bn, pending=1)
 
 
 def mrla_light_block_tail(out, identity, mrla: mrla_module, bn: nn.BatchNorm2d, drop_path: nn.Module,
@@ -56,6 +56,15 @@ def mrla_light_block_tail(out, identity, mrla: mrla_module, bn: nn.BatchNorm2d, 
     Where the library folds it, bn3 becomes statistics + a per-channel affine applied inside sweep 1 (one autograd node
     for bn3 + add + ReLU + tail); otherwise bn3 runs as its own op first."""
     layer = mrla.mrla
+    if not is_plain_batchnorm(bn):
+        # norm_layer = SyncBatchNorm / GroupNorm / frozen BN ...: keep the norm module's own semantics (cross-rank
+        # statistics, group statistics).  The MRLA module still runs on the fused kernels; bn / drop_path / residual are
+        # the reference's own sequence (resnet_mrla_light.py:101-102,113-116).
+        if pre_bn is not None:
+            out = bn_act(out, pre_bn)
+        if pre_add_relu:
+            out = torch.relu(out + identity)
+        return out + drop_path(bn(mrla(out, identity)))
     use_batch_stats = bn.training or bn.running_mean is None
     if use_batch_stats:
         mode = _lib.BN_TRAIN

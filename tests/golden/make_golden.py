@@ -233,14 +233,33 @@ CASES = {
     "deit_light_c64": (deit_light_case, dict(seed=13, B=3, S=4, C=64, d=16)),
     "deit_light_c192": (deit_light_case, dict(seed=14, B=2, S=3, C=192, d=16)),
     "deit_base_c64_t3": (deit_base_case, dict(seed=15, B=2, S=4, C=64, d=16, T=3)),
+    # DeiT-tiny geometry of BASELINE configs[4]: 197 tokens (14x14 + cls), C = 192, 12 heads of 16 (round 2)
+    "deit_light_c192_n197": (deit_light_case, dict(seed=16, B=2, S=14, C=192, d=16)),
+    "deit_base_c192_t2_n197": (deit_base_case, dict(seed=17, B=2, S=14, C=192, d=16, T=2)),
 }
+F32_OUTPUTS = {"deit_light_c192_n197", "deit_base_c192_t2_n197"}   # outputs / gradients stored in fp32 (file size)
+
+
+def _to_f32(obj):
+    if isinstance(obj, torch.Tensor) and obj.dtype == torch.float64:
+        return obj.float()
+    if isinstance(obj, dict):
+        return {k: _to_f32(v) for k, v in obj.items()}
+    if isinstance(obj, list):
+        return [_to_f32(v) for v in obj]
+    return obj
 
 
 def main():
     assert ref_loader.available(), "reference tree not found (set MRLA_REF)"
     total = 0
+    only = set(sys.argv[1:])
     for name, (fn, kw) in CASES.items():
+        if only and name not in only:
+            continue
         case = fn(**kw)
+        if name in F32_OUTPUTS:
+            case = _to_f32(case)
         path = os.path.join(HERE, name + ".pt.gz")
         with gzip.open(path, "wb", compresslevel=9) as f:
             torch.save(case, f)

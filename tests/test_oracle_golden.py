@@ -9,6 +9,11 @@ from oracle import mrla_oracle as O
 TOL = 1e-11
 
 
+def _t(ref, base):
+    """Fixtures whose outputs are stored in fp32 (the 197-token DeiT cases, file size) carry fp32 rounding of the reference."""
+    return max(base, 2e-6) if ref.dtype == torch.float32 else base
+
+
 def _leaf(t):
     return t.clone().requires_grad_()
 
@@ -85,10 +90,10 @@ def test_base_stage(name):
     loss.backward()
     assert rel_err(k, g["K"]) < TOL and rel_err(v, g["V"]) < TOL
     for t in range(T):
-        assert rel_err(ys[t], g["ys"][t]) < TOL
-        assert rel_err(xs[t].grad, g["dxs"][t]) < 1e-10
+        assert rel_err(ys[t], g["ys"][t]) < _t(g["ys"][t], TOL)
+        assert rel_err(xs[t].grad, g["dxs"][t]) < _t(g["ys"][t], 1e-10)
         for n in Ps[t]:
-            assert rel_err(Ps[t][n].grad, g["blocks"][t]["dparams"][n]) < 1e-10, (t, n)
+            assert rel_err(Ps[t][n].grad, g["blocks"][t]["dparams"][n]) < _t(g["ys"][t], 1e-10), (t, n)
 
 
 @pytest.mark.parametrize("name", golden_names("deit_light"))
@@ -100,11 +105,11 @@ def test_deit_light(name):
     y = O.deit_light_block_tail(x, o, P["mrla.Wq.weight"], P["mrla.Wk.weight"], P["mrla.Wv.weight"], P["lambda_t"],
                                 heads, P["normx.weight"], P["normx.bias"], P["normo.weight"], P["normo.bias"])
     (y * g["dy"]).sum().backward()
-    assert rel_err(y, g["y"]) < TOL
-    assert rel_err(x.grad, g["dx"]) < 1e-10
-    assert rel_err(o.grad, g["do"]) < 1e-10
+    assert rel_err(y, g["y"]) < _t(g["y"], TOL)
+    assert rel_err(x.grad, g["dx"]) < _t(g["y"], 1e-10)
+    assert rel_err(o.grad, g["do"]) < _t(g["y"], 1e-10)
     for k in P:
-        assert rel_err(P[k].grad, g["dparams"][k]) < 1e-10, k
+        assert rel_err(P[k].grad, g["dparams"][k]) < _t(g["y"], 1e-10), k
 
 
 @pytest.mark.parametrize("name", golden_names("deit_base"))
@@ -125,7 +130,7 @@ def test_deit_base(name):
         loss = loss + (y * g["dys"][t]).sum()
     loss.backward()
     for t in range(T):
-        assert rel_err(ys[t], g["ys"][t]) < TOL
-        assert rel_err(xs[t].grad, g["dxs"][t]) < 1e-10
+        assert rel_err(ys[t], g["ys"][t]) < _t(g["ys"][t], TOL)
+        assert rel_err(xs[t].grad, g["dxs"][t]) < _t(g["ys"][t], 1e-10)
         for n in Ps[t]:
-            assert rel_err(Ps[t][n].grad, g["blocks"][t]["dparams"][n]) < 1e-10, (t, n)
+            assert rel_err(Ps[t][n].grad, g["blocks"][t]["dparams"][n]) < _t(g["ys"][t], 1e-10), (t, n)
