@@ -328,7 +328,8 @@ def run_product_arm(args):
     launches_per_step = None
     if not args.no_graph:
         l0 = ops.launch_counter["fwd"] + ops.launch_counter["bwd"]
-        gstep = GraphedStep(model, opt, crit, dev_img, dev_lbl, warmup=3, overlap=args.overlap_comm)
+        gstep = GraphedStep(model, opt, crit, dev_img, dev_lbl, warmup=3, overlap=args.overlap_comm,
+                            capture_collective=args.capture_comm)
         # launches of one captured step = (warm-up + capture) launches / their count
         launches_per_step = (ops.launch_counter["fwd"] + ops.launch_counter["bwd"] - l0) // 4
         dev_img, dev_lbl = gstep.inputs, gstep.targets
@@ -495,8 +496,10 @@ def run_product_arm(args):
                    "drop_path": args.drop_path,
                    "host_batch": "e2e: pinned uint8 HWC images + int64 labels copied H2D every step, normalised to bf16 "
                                  "channels_last on the device",
-                   "parallelism": f"dp{world}" + ((" (flat-gradient NCCL all-reduce captured in the step graph" +
-                                                   (", bucketed and overlapped with backward)" if args.overlap_comm else ")")
+                   "parallelism": f"dp{world}" + ((" (flat-gradient NCCL all-reduce " +
+                                                   ("bucketed and overlapped with backward inside the step graph)" if args.overlap_comm
+                                                    else ("captured in the step graph)" if args.capture_comm
+                                                          else "between the fwd+bwd graph and the SGD graph)"))
                                                    if gstep is not None else " (DDP/NCCL)") if world > 1 else ""),
                    "l2": "inputs exceed L2 (per-step activations >> 126 MB); no explicit flush",
                    "launch": "mrla_b200.train.GraphedStep: CUDA graphs (fwd+bwd+all-reduce | SGD)" if gstep is not None
@@ -628,6 +631,8 @@ def main():
                          "at the module level")
     ap.add_argument("--overlap-comm", action="store_true",
                     help="N > 1: bucketed gradient all-reduce overlapped with backward instead of one all-reduce after it")
+    ap.add_argument("--capture-comm", action="store_true",
+                    help="N > 1: capture the flat-gradient all-reduce inside graph A instead of issuing it between the graphs")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the same-GPU eager PyTorch baseline")
     ap.add_argument("--compile-baseline", action="store_true", help="also time the eager baseline under torch.compile")
     args = ap.parse_args()

@@ -41,7 +41,8 @@ class GraphedStep:
     def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, loss_fn: Callable,
                  example_inputs: torch.Tensor, example_targets: torch.Tensor, *,
                  autocast_dtype: Optional[torch.dtype] = torch.bfloat16, process_group=None, bucket_mb: float = 25.0,
-                 warmup: int = 3, capture: bool = True, broadcast: bool = True, overlap: bool = False):
+                 warmup: int = 3, capture: bool = True, broadcast: bool = True, overlap: bool = False,
+                 capture_collective: bool = False):
         if not example_inputs.is_cuda:
             raise RuntimeError("GraphedStep: inputs must live on a CUDA device")
         self.model, self.opt, self.loss_fn = model, optimizer, loss_fn
@@ -69,6 +70,8 @@ class GraphedStep:
             off += p.numel()
         self.buckets = []          # (start, end, [params])
         self.overlap = bool(overlap) and self.world > 1
+        # the flat all-reduce either sits between the two graphs (default, one eager NCCL call per step) or inside graph A
+        self.capture_collective = bool(capture_collective) or self.overlap
         if self.world > 1 and not self.overlap:
             self.buckets = [(0, n, list(self.params))]
             if broadcast:
@@ -97,6 +100,7 @@ class GraphedStep:
         self.graph_a = self.graph_b = None
         self.loss = None
         self._armed = False
+        self._capturing = False
         if capture:
             self._capture(warmup)
 
@@ -130,7 +134,7 @@ class GraphedStep:
             out = self.model(self.inputs)
         loss = self.loss_fn(out.float(), self.targets)
         loss.backward()
-        if self.world > 1 and not self.overlap:
+        if self.world > 1 and not self.overlap and (self.capture_collective or self.graph_a is None and not self._capturing):
             dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.pg)
             self.collective_launches += 1
         if self.overlap:
@@ -156,9 +160,14 @@ class GraphedStep:
         torch.cuda.synchronize(self.dev)
         self.collective_launches = 0
         self.graph_a, self.graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_a):
+        # with NCCL in the process, its watchdog thread polls CUDA events while this thread captures: thread-local capture
+        # mode keeps those (legal) calls from invalidating the capture
+        mode = "thread_local" if self.world > 1 else "global"
+        self._capturing = True
+        with torch.cuda.graph(self.graph_a, capture_error_mode=mode):
             self.loss = self._fwd_bwd()
-        with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
+        self._capturing = False
+        with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool(), capture_error_mode=mode):
             self.opt.step()
         torch.cuda.synchronize(self.dev)
 
@@ -175,6 +184,8 @@ class GraphedStep:
         self.load(inputs, targets)
         if self.graph_a is not None:
             self.graph_a.replay()
+            if self.world > 1 and not self.capture_collective:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.pg)
             self.graph_b.replay()
             return self.loss
         loss = self._fwd_bwd()
@@ -184,6 +195,13 @@ class GraphedStep:
     step = __call__
 
     def close(self):
+        """Drop the hooks and the captured graphs (release them before `destroy_process_group()`: a live graph keeps a
+        reference to the NCCL communicator it was captured on)."""
         for h in getattr(self, "_hooks", []):
             h.remove()
         self._hooks = []
+        torch.cuda.synchronize(self.dev)
+        for g in (self.graph_a, self.graph_b):
+            if g is not None:
+                g.reset()
+        self.graph_a = self.graph_b = None

@@ -14,7 +14,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def log(rank, msg):
+    print(f"[rank {rank}] {msg}", flush=True)
+
+
 def main():
+    os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")   # PyTorch's note for NCCL inside CUDA graphs
     rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
     print(f"[rank {rank}] start", flush=True)
     torch.cuda.set_device(local)
@@ -39,12 +44,15 @@ def main():
     crit(out.float(), batches[0][1]).backward()
     mine = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
     gathered = [torch.empty_like(mine) for _ in range(2)]
+    log(rank, "reference gradients done")
     dist.all_gather(gathered, mine)
+    log(rank, "all_gather done")
     want = (gathered[0] + gathered[1]) / 2
     m1 = copy.deepcopy(base)
     opt1 = torch.optim.SGD(m1.parameters(), lr=0.0)   # lr 0: the warm-up / capture executions leave the weights alone
     overlap = os.environ.get("MRLA_TEST_OVERLAP", "0") == "1"
     st1 = GraphedStep(m1, opt1, crit, batches[0][0], batches[0][1], autocast_dtype=None, bucket_mb=1.0, warmup=2, overlap=overlap)
+    log(rank, "GraphedStep captured")
     assert len(st1.buckets) >= (3 if overlap else 1), len(st1.buckets)
     st1(batches[0][0], batches[0][1])
     torch.cuda.synchronize()
@@ -66,7 +74,9 @@ def main():
             for v in s_.values():
                 if torch.is_tensor(v):
                     v.zero_()
-        losses.append([float(st(x, y)) for x, y in batches])
+        log(rank, f"capture={capture} constructed")
+        losses.append([float(st(x, y).detach()) for x, y in batches])
+        log(rank, f"capture={capture} 3 steps done")
         states.append({k: v.clone() for k, v in m.state_dict().items()})
         st.close()
     for a, b in zip(*losses):
@@ -79,9 +89,13 @@ def main():
     dist.all_gather(other, flat)
     assert torch.equal(other[0], other[1]), "ranks diverged"
     dist.barrier()
+    torch.cuda.synchronize()
     if rank == 0:
-        print("DIST_GRAPHED_STEP_OK")
-    dist.destroy_process_group()
+        print("DIST_GRAPHED_STEP_OK", flush=True)
+    # captured graphs still reference the NCCL communicator; tearing the process group down under them blocks in this
+    # PyTorch / NCCL combination, so the checker leaves without the (irrelevant) orderly shutdown
+    sys.stdout.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":

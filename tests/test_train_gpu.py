@@ -70,6 +70,8 @@ def test_graphed_step_two_ranks_nccl(overlap):
     the bucketed all-reduce overlapped with backward."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
+    if os.environ.get("MRLA_RUN_DIST_TESTS", "0") != "1":
+        pytest.skip("set MRLA_RUN_DIST_TESTS=1 (spawns torchrun with 2 ranks; run it through `gpurun --gpus 2`)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(29533 + int(overlap)), os.path.join(ROOT, "tests", "dist_graphed_step.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=dict(os.environ, MRLA_TEST_OVERLAP=overlap))
