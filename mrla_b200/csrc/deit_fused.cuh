@@ -67,8 +67,10 @@ __device__ __forceinline__ void ln_stats(const float2 (&v)[kDeitMaxCJ], int CJ, 
 }
 
 // shared memory: xn tile [n][C] (T) | ys[C] | qk[C] | kq[2][C] | gate[g<=64] | sx[n] float2 | so[n] float2 | red scratch
-template <typename T>
-__global__ void __launch_bounds__(384) k_deit_light_fwd(const DeitParams P) {
+// MAXT = 192: two CTAs per SM (all 256 samples of a DeiT-tiny batch are resident at once and the memory-latency-bound
+// LayerNorm phases of one CTA overlap the arithmetic phases of the other); MAXT = 384: wider models, one CTA per SM
+template <typename T, int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT == 192 ? 2 : 1) k_deit_light_fwd(const DeitParams P) {
   constexpr int ES = sizeof(T);
   constexpr int K = kV7;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -84,36 +86,63 @@ __global__ void __launch_bounds__(384) k_deit_light_fwd(const DeitParams P) {
   const T* ob = static_cast<const T*>(P.o) + (int64_t)b * n * C;
   T* outb = static_cast<T*>(P.out) + (int64_t)b * n * C;
 
-  // ---- phase 1: LayerNorm of every token of x (normalised values -> shared memory) and statistics of o
-  for (int t = warp; t < n; t += nw) {
-    float2 v[kDeitMaxCJ];
+  // ---- phase 1: LayerNorm of every token of x (normalised values -> shared memory) and statistics of o.
+  // A warp owns tokens warp, warp+nw, ...; the loads of two tokens (x and o) are issued before any reduction so that
+  // eight 128-byte requests per lane are in flight, and the GAP sums of the image tokens are taken from the registers.
+  float* red = reinterpret_cast<float*>(so + n);   // [nw][C] GAP partials
+  float2 gsum[kDeitMaxCJ];
 #pragma unroll
-    for (int j = 0; j < kDeitMaxCJ; ++j) if (j < CJ) v[j] = ldg_pair<T>(xb + (int64_t)t * C + 2 * (j * 32 + lane));
-    float mean, rstd;
-    ln_stats(v, CJ, C, P.eps, mean, rstd);
+  for (int j = 0; j < kDeitMaxCJ; ++j) gsum[j] = f2(0.f, 0.f);
+  for (int t0 = warp; t0 < n; t0 += 2 * nw) {
+    float2 vx[2][kDeitMaxCJ], vo[2][kDeitMaxCJ];
 #pragma unroll
-    for (int j = 0; j < kDeitMaxCJ; ++j) if (j < CJ) {
-      const int c = 2 * (j * 32 + lane);
-      const float2 gm = *reinterpret_cast<const float2*>(P.gx + c), bt = *reinterpret_cast<const float2*>(P.bx + c);
-      const float2 y = f2((v[j].x - mean) * rstd * gm.x + bt.x, (v[j].y - mean) * rstd * gm.y + bt.y);
-      sts_pair_t<T>(xn_s + (uint32_t)(t * C + c) * ES, y);
-      if (t == 0) stg_pair<T>(outb + c, y);   // cls row of the output is LN_x(x)[:, 0] (deit_mrla_light.py:207)
+    for (int u = 0; u < 2; ++u) {
+      const int t = t0 + u * nw;
+#pragma unroll
+      for (int j = 0; j < kDeitMaxCJ; ++j)
+        if (j < CJ && t < n) {
+          vx[u][j] = ldg_pair<T>(xb + (int64_t)t * C + 2 * (j * 32 + lane));
+          vo[u][j] = ldg_pair<T>(ob + (int64_t)t * C + 2 * (j * 32 + lane));
+        }
     }
 #pragma unroll
-    for (int j = 0; j < kDeitMaxCJ; ++j) if (j < CJ) v[j] = ldg_pair<T>(ob + (int64_t)t * C + 2 * (j * 32 + lane));
-    float mo, ro;
-    ln_stats(v, CJ, C, P.eps, mo, ro);
-    if (lane == 0) {
-      so[t] = f2(mo, ro);
-      *reinterpret_cast<float2*>(P.stats_x + ((int64_t)b * n + t) * 2) = f2(mean, rstd);
-      *reinterpret_cast<float2*>(P.stats_o + ((int64_t)b * n + t) * 2) = f2(mo, ro);
+    for (int u = 0; u < 2; ++u) {
+      const int t = t0 + u * nw;
+      if (t < n) {
+        float mean, rstd, mo, ro;
+        ln_stats(vx[u], CJ, C, P.eps, mean, rstd);
+        ln_stats(vo[u], CJ, C, P.eps, mo, ro);
+#pragma unroll
+        for (int j = 0; j < kDeitMaxCJ; ++j)
+          if (j < CJ) {
+            const int c = 2 * (j * 32 + lane);
+            const float2 gm = *reinterpret_cast<const float2*>(P.gx + c), bt = *reinterpret_cast<const float2*>(P.bx + c);
+            const float2 y = f2((vx[u][j].x - mean) * rstd * gm.x + bt.x, (vx[u][j].y - mean) * rstd * gm.y + bt.y);
+            const typename RawPair<T>::type yr = pack_pair<T>(y);
+            sts_raw(xn_s + (uint32_t)(t * C + c) * ES, yr);
+            if (t == 0) {
+              stg_raw<T>(outb + c, yr);   // cls row of the output is LN_x(x)[:, 0] (deit_mrla_light.py:207)
+            } else {
+              const float2 ys_ = unpack_pair<T>(yr);   // the GAP averages the STORED (rounded) values, like the reference
+              gsum[j] = f2(gsum[j].x + ys_.x, gsum[j].y + ys_.y);
+            }
+          }
+        if (lane == 0) {
+          so[t] = f2(mo, ro);
+          *reinterpret_cast<float2*>(P.stats_x + ((int64_t)b * n + t) * 2) = f2(mean, rstd);
+          *reinterpret_cast<float2*>(P.stats_o + ((int64_t)b * n + t) * 2) = f2(mo, ro);
+        }
+      }
     }
   }
+#pragma unroll
+  for (int j = 0; j < kDeitMaxCJ; ++j)
+    if (j < CJ) *reinterpret_cast<float2*>(red + (size_t)warp * C + 2 * (j * 32 + lane)) = gsum[j];
   __syncthreads();
   // ---- phase 2: GAP over the S*S image tokens, ECA conv1d pair over the channel axis, per-head sigmoid gate
   for (int c = tid; c < C; c += blockDim.x) {
     float s = 0.f;
-    for (int t = 1; t < n; ++t) s += to_f<T>(*reinterpret_cast<const T*>(xn + (size_t)(t * C + c) * ES));
+    for (int w = 0; w < nw; ++w) s += red[(size_t)w * C + c];
     ys[c] = s / (float)(n - 1);
   }
   __syncthreads();
@@ -160,8 +189,21 @@ __global__ void __launch_bounds__(384) k_deit_light_fwd(const DeitParams P) {
     }
   };
   load_row(0, win[1]);
+  float2 onext[K];
+  auto load_o = [&](int h, float2 (&dst)[K]) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const int w = q * K + j;
+      dst[j] = (h < S && w < S) ? ldg_pair<T>(ob + (int64_t)(1 + h * S + w) * C + c) : f2(0.f, 0.f);
+    }
+  };
+  load_o(0, onext);
   for (int h = 0; h < S; ++h) {
     load_row(h + 1, win[2]);
+    float2 ocur[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) ocur[j] = onext[j];
+    load_o(h + 1, onext);   // in flight while this row is computed
 #pragma unroll
     for (int j = 0; j < K; ++j) {
       const int w = q * K + j;
@@ -169,7 +211,7 @@ __global__ void __launch_bounds__(384) k_deit_light_fwd(const DeitParams P) {
         const float2 u = conv9n<K + 2>(win[0], win[1], win[2], w9, j);
         const float2 v = f2(act_fwd<1>(u.x), act_fwd<1>(u.y));
         const int t = 1 + h * S + w;
-        const float2 ov = ldg_pair<T>(ob + (int64_t)t * C + c);
+        const float2 ov = ocur[j];
         const float2 st = so[t];
         const float2 on = f2((ov.x - st.x) * st.y * go2.x + bo2.x, (ov.y - st.x) * st.y * go2.y + bo2.y);
         stg_pair<T>(outb + (int64_t)t * C + c, f2(fmaf(a2.x, v.x, lm.x * on.x), fmaf(a2.y, v.y, lm.y * on.y)));
@@ -183,8 +225,8 @@ __global__ void __launch_bounds__(384) k_deit_light_fwd(const DeitParams P) {
 // =====================================================================================================
 // backward.  d_out [B,n,C] -> dx, do [B,n,C] and per-sample parameter partials.
 // =====================================================================================================
-template <typename T>
-__global__ void __launch_bounds__(384) k_deit_light_bwd(const DeitParams P) {
+template <typename T, int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT == 192 ? 2 : 1) k_deit_light_bwd(const DeitParams P) {
   constexpr int ES = sizeof(T);
   constexpr int K = kV7;
   constexpr int KT = K + 2, KX = K + 4;
@@ -211,22 +253,51 @@ __global__ void __launch_bounds__(384) k_deit_light_bwd(const DeitParams P) {
   const float* sog = P.stats_o + (int64_t)b * n * 2;
   float* part = P.part + (int64_t)b * P.PW;
 
-  // ---- phase 1: recompute xn = LN_x(x) from the saved statistics
-  for (int t = warp; t < n; t += nw) {
-    const float2 st = *reinterpret_cast<const float2*>(sxg + 2 * t);
+  // ---- phase 1: recompute xn = LN_x(x) from the saved statistics (two tokens in flight per warp), GAP from registers
+  {
+    float2 gsum[kDeitMaxCJ];
 #pragma unroll
-    for (int j = 0; j < kDeitMaxCJ; ++j) if (j < CJ) {
-      const int c = 2 * (j * 32 + lane);
-      const float2 v = ldg_pair<T>(xb + (int64_t)t * C + c);
-      const float2 gm = *reinterpret_cast<const float2*>(P.gx + c), bt = *reinterpret_cast<const float2*>(P.bx + c);
-      sts_pair_t<T>(xn_s + (uint32_t)(t * C + c) * ES, f2((v.x - st.x) * st.y * gm.x + bt.x, (v.y - st.x) * st.y * gm.y + bt.y));
+    for (int j = 0; j < kDeitMaxCJ; ++j) gsum[j] = f2(0.f, 0.f);
+    for (int t0 = warp; t0 < n; t0 += 2 * nw) {
+      float2 vx[2][kDeitMaxCJ];
+      float2 st[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int t = t0 + u * nw;
+        st[u] = (t < n) ? *reinterpret_cast<const float2*>(sxg + 2 * t) : f2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < kDeitMaxCJ; ++j)
+          if (j < CJ && t < n) vx[u][j] = ldg_pair<T>(xb + (int64_t)t * C + 2 * (j * 32 + lane));
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int t = t0 + u * nw;
+        if (t < n) {
+#pragma unroll
+          for (int j = 0; j < kDeitMaxCJ; ++j)
+            if (j < CJ) {
+              const int c = 2 * (j * 32 + lane);
+              const float2 gm = *reinterpret_cast<const float2*>(P.gx + c), bt = *reinterpret_cast<const float2*>(P.bx + c);
+              const typename RawPair<T>::type yr = pack_pair<T>(f2((vx[u][j].x - st[u].x) * st[u].y * gm.x + bt.x,
+                                                                   (vx[u][j].y - st[u].x) * st[u].y * gm.y + bt.y));
+              sts_raw(xn_s + (uint32_t)(t * C + c) * ES, yr);
+              if (t >= 1) {
+                const float2 ys_ = unpack_pair<T>(yr);
+                gsum[j] = f2(gsum[j].x + ys_.x, gsum[j].y + ys_.y);
+              }
+            }
+        }
+      }
     }
+#pragma unroll
+    for (int j = 0; j < kDeitMaxCJ; ++j)
+      if (j < CJ) *reinterpret_cast<float2*>(red + (size_t)warp * C + 2 * (j * 32 + lane)) = gsum[j];
   }
   if (tid < g) gate[tid] = P.gate[(int64_t)b * g + tid];
   __syncthreads();
   for (int c = tid; c < C; c += blockDim.x) {
     float s = 0.f;
-    for (int t = 1; t < n; ++t) s += to_f<T>(*reinterpret_cast<const T*>(xn + (size_t)(t * C + c) * ES));
+    for (int w = 0; w < nw; ++w) s += red[(size_t)w * C + c];
     ys[c] = s / (float)(n - 1);
   }
   __syncthreads();
@@ -241,6 +312,7 @@ __global__ void __launch_bounds__(384) k_deit_light_bwd(const DeitParams P) {
     qv[c] = q;
     kv[c] = kk;
   }
+  __syncthreads();   // the GAP partials in `red` have been consumed: phase 2 reuses the scratch
   // ---- phase 2: sum_t dS*V per channel (V recomputed) -> gate gradient -> GAP gradient
   const int p = tid % NP, q = tid / NP;
   const bool worker = q < P.NQ;
@@ -259,15 +331,21 @@ __global__ void __launch_bounds__(384) k_deit_light_bwd(const DeitParams P) {
     float2 win[3][K + 2];
 #pragma unroll
     for (int j = 0; j < K + 2; ++j) { win[0][j] = f2(0.f, 0.f); win[1][j] = xrow(0, q * K - 1 + j); }
+    float2 gnext[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) gnext[j] = grow(0, q * K + j);
     for (int h = 0; h < S; ++h) {
 #pragma unroll
       for (int j = 0; j < K + 2; ++j) win[2][j] = xrow(h + 1, q * K - 1 + j);
+      float2 gcur[K];
+#pragma unroll
+      for (int j = 0; j < K; ++j) { gcur[j] = gnext[j]; gnext[j] = grow(h + 1, q * K + j); }   // next row in flight
 #pragma unroll
       for (int j = 0; j < K; ++j) {
         const int w = q * K + j;
         if (w < S) {
           const float2 u = conv9n<K + 2>(win[0], win[1], win[2], w9, j);
-          const float2 ds = grow(h, w);
+          const float2 ds = gcur[j];
           acc.x = fmaf(ds.x, act_fwd<1>(u.x), acc.x);
           acc.y = fmaf(ds.y, act_fwd<1>(u.y), acc.y);
         }
@@ -337,13 +415,18 @@ __global__ void __launch_bounds__(384) k_deit_light_bwd(const DeitParams P) {
       for (int j = 0; j < KX; ++j) xw[1][j] = xrow(0, q * K - 2 + j);
     }
     // step s: fetch x row s; dU row s-1; scatter; dX row s-2 complete
+    float2 gnext[KT];
+#pragma unroll
+    for (int j = 0; j < KT; ++j) gnext[j] = worker ? grow(0, q * K - 1 + j) : f2(0.f, 0.f);
     for (int s = 1; s <= S + 1; ++s) {
       float2 done[K];
       if (worker) {
 #pragma unroll
         for (int j = 0; j < KX; ++j) xw[2][j] = xrow(s, q * K - 2 + j);
-        float2 tt[KT];
+        float2 tt[KT], gcur[KT];
         const int t = s - 1;
+#pragma unroll
+        for (int j = 0; j < KT; ++j) { gcur[j] = gnext[j]; gnext[j] = grow(s, q * K - 1 + j); }   // row t+1 in flight
 #pragma unroll
         for (int j = 0; j < KT; ++j) {
           const int w = q * K - 1 + j;
@@ -353,7 +436,7 @@ __global__ void __launch_bounds__(384) k_deit_light_bwd(const DeitParams P) {
             u = ffma2(w9[1], xw[0][j + 1], u); u = ffma2(w9[2], xw[0][j + 2], u);
             u = ffma2(w9[3], xw[1][j], u); u = ffma2(w9[4], xw[1][j + 1], u); u = ffma2(w9[5], xw[1][j + 2], u);
             u = ffma2(w9[6], xw[2][j], u); u = ffma2(w9[7], xw[2][j + 1], u); u = ffma2(w9[8], xw[2][j + 2], u);
-            const float2 ds = grow(t, w);
+            const float2 ds = gcur[j];
             tt[j] = f2(a2.x * ds.x * act_grad<1>(u.x), a2.y * ds.y * act_grad<1>(u.y));
             if (j >= 1 && j <= K) {
               dwv[0] = ffma2(tt[j], xw[0][j], dwv[0]); dwv[1] = ffma2(tt[j], xw[0][j + 1], dwv[1]); dwv[2] = ffma2(tt[j], xw[0][j + 2], dwv[2]);
@@ -408,64 +491,86 @@ __global__ void __launch_bounds__(384) k_deit_light_bwd(const DeitParams P) {
     part[cc * 9 + i] = s;
   }
   __syncthreads();
-  // ---- phase 4: both LayerNorm backwards, one token per warp; per-lane channel sums for d(gamma), d(beta), d(lambda)
+  // ---- phase 4: both LayerNorm backwards, one token per warp (the loads of two tokens are issued together); per-lane
+  // channel sums for d(gamma), d(beta), d(lambda)
   float2 sgx[kDeitMaxCJ], sbx[kDeitMaxCJ], sgo[kDeitMaxCJ], sbo[kDeitMaxCJ], slm[kDeitMaxCJ];
+#pragma unroll
   for (int j = 0; j < kDeitMaxCJ; ++j) { sgx[j] = sbx[j] = sgo[j] = sbo[j] = slm[j] = f2(0.f, 0.f); }
   const float invC = 1.f / (float)C;
-  for (int t = warp; t < n; t += nw) {
-    // LN_x
-    {
-      const float2 st = *reinterpret_cast<const float2*>(sxg + 2 * t);
-      float2 xh[kDeitMaxCJ], gg[kDeitMaxCJ];
-      float s1 = 0.f, s2 = 0.f;
+  for (int t0 = warp; t0 < n; t0 += 2 * nw) {
+    float2 vx[2][kDeitMaxCJ], vo[2][kDeitMaxCJ], vg[2][kDeitMaxCJ];
+    float2 stx[2], sto[2];
 #pragma unroll
-      for (int j = 0; j < kDeitMaxCJ; ++j) if (j < CJ) {
-        const int cc = 2 * (j * 32 + lane);
-        const float2 v = ldg_pair<T>(xb + (int64_t)t * C + cc);
-        const float2 dxn = lds_pair<T>(xn_s + (uint32_t)(t * C + cc) * ES);
-        const float2 gm = *reinterpret_cast<const float2*>(P.gx + cc);
-        xh[j] = f2((v.x - st.x) * st.y, (v.y - st.x) * st.y);
-        gg[j] = f2(dxn.x * gm.x, dxn.y * gm.y);
-        s1 += gg[j].x + gg[j].y;
-        s2 = fmaf(gg[j].x, xh[j].x, fmaf(gg[j].y, xh[j].y, s2));
-        sgx[j] = f2(fmaf(dxn.x, xh[j].x, sgx[j].x), fmaf(dxn.y, xh[j].y, sgx[j].y));
-        sbx[j] = f2(sbx[j].x + dxn.x, sbx[j].y + dxn.y);
+    for (int u = 0; u < 2; ++u) {
+      const int t = t0 + u * nw;
+      stx[u] = sto[u] = f2(0.f, 0.f);
+      if (t < n) {
+        stx[u] = *reinterpret_cast<const float2*>(sxg + 2 * t);
+        sto[u] = *reinterpret_cast<const float2*>(sog + 2 * t);
       }
-      s1 = warp_sum(s1) * invC;
-      s2 = warp_sum(s2) * invC;
 #pragma unroll
-      for (int j = 0; j < kDeitMaxCJ; ++j) if (j < CJ) {
-        const int cc = 2 * (j * 32 + lane);
-        stg_pair<T>(dxb + (int64_t)t * C + cc, f2(st.y * (gg[j].x - s1 - xh[j].x * s2), st.y * (gg[j].y - s1 - xh[j].y * s2)));
-      }
+      for (int j = 0; j < kDeitMaxCJ; ++j)
+        if (j < CJ && t < n) {
+          const int cc = 2 * (j * 32 + lane);
+          vx[u][j] = ldg_pair<T>(xb + (int64_t)t * C + cc);
+          vo[u][j] = ldg_pair<T>(ob + (int64_t)t * C + cc);
+          vg[u][j] = (t >= 1) ? ldg_pair<T>(gb + (int64_t)t * C + cc) : f2(0.f, 0.f);
+        }
     }
-    // LN_o : d(on) = lambda * dS for image tokens, 0 for the cls token (its `on` row is unused, deit_mrla_light.py:204-207)
-    {
-      const float2 st = *reinterpret_cast<const float2*>(sog + 2 * t);
-      float2 oh[kDeitMaxCJ], gg[kDeitMaxCJ];
-      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int j = 0; j < kDeitMaxCJ; ++j) if (j < CJ) {
-        const int cc = 2 * (j * 32 + lane);
-        const float2 v = ldg_pair<T>(ob + (int64_t)t * C + cc);
-        const float2 ds = (t >= 1) ? ldg_pair<T>(gb + (int64_t)t * C + cc) : f2(0.f, 0.f);
-        const float2 lm = *reinterpret_cast<const float2*>(P.lam + cc);
-        const float2 gm = *reinterpret_cast<const float2*>(P.go + cc), bt = *reinterpret_cast<const float2*>(P.bo + cc);
-        oh[j] = f2((v.x - st.x) * st.y, (v.y - st.x) * st.y);
-        const float2 don = f2(lm.x * ds.x, lm.y * ds.y);
-        gg[j] = f2(don.x * gm.x, don.y * gm.y);
-        s1 += gg[j].x + gg[j].y;
-        s2 = fmaf(gg[j].x, oh[j].x, fmaf(gg[j].y, oh[j].y, s2));
-        sgo[j] = f2(fmaf(don.x, oh[j].x, sgo[j].x), fmaf(don.y, oh[j].y, sgo[j].y));
-        sbo[j] = f2(sbo[j].x + don.x, sbo[j].y + don.y);
-        slm[j] = f2(fmaf(ds.x, oh[j].x * gm.x + bt.x, slm[j].x), fmaf(ds.y, oh[j].y * gm.y + bt.y, slm[j].y));
-      }
-      s1 = warp_sum(s1) * invC;
-      s2 = warp_sum(s2) * invC;
+    for (int u = 0; u < 2; ++u) {
+      const int t = t0 + u * nw;
+      if (t < n) {
+        // LN_x
+        float2 xh[kDeitMaxCJ], gg[kDeitMaxCJ];
+        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int j = 0; j < kDeitMaxCJ; ++j) if (j < CJ) {
-        const int cc = 2 * (j * 32 + lane);
-        stg_pair<T>(dob + (int64_t)t * C + cc, f2(st.y * (gg[j].x - s1 - oh[j].x * s2), st.y * (gg[j].y - s1 - oh[j].y * s2)));
+        for (int j = 0; j < kDeitMaxCJ; ++j)
+          if (j < CJ) {
+            const int cc = 2 * (j * 32 + lane);
+            const float2 dxn = lds_pair<T>(xn_s + (uint32_t)(t * C + cc) * ES);
+            const float2 gm = *reinterpret_cast<const float2*>(P.gx + cc);
+            xh[j] = f2((vx[u][j].x - stx[u].x) * stx[u].y, (vx[u][j].y - stx[u].x) * stx[u].y);
+            gg[j] = f2(dxn.x * gm.x, dxn.y * gm.y);
+            s1 += gg[j].x + gg[j].y;
+            s2 = fmaf(gg[j].x, xh[j].x, fmaf(gg[j].y, xh[j].y, s2));
+            sgx[j] = f2(fmaf(dxn.x, xh[j].x, sgx[j].x), fmaf(dxn.y, xh[j].y, sgx[j].y));
+            sbx[j] = f2(sbx[j].x + dxn.x, sbx[j].y + dxn.y);
+          }
+        s1 = warp_sum(s1) * invC;
+        s2 = warp_sum(s2) * invC;
+#pragma unroll
+        for (int j = 0; j < kDeitMaxCJ; ++j)
+          if (j < CJ) {
+            const int cc = 2 * (j * 32 + lane);
+            stg_pair<T>(dxb + (int64_t)t * C + cc, f2(stx[u].y * (gg[j].x - s1 - xh[j].x * s2), stx[u].y * (gg[j].y - s1 - xh[j].y * s2)));
+          }
+        // LN_o : d(on) = lambda * dS for image tokens, 0 for the cls token (its `on` row is unused, deit_mrla_light.py:204-207)
+        float o1 = 0.f, o2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < kDeitMaxCJ; ++j)
+          if (j < CJ) {
+            const int cc = 2 * (j * 32 + lane);
+            const float2 ds = vg[u][j];
+            const float2 lm = *reinterpret_cast<const float2*>(P.lam + cc);
+            const float2 gm = *reinterpret_cast<const float2*>(P.go + cc), bt = *reinterpret_cast<const float2*>(P.bo + cc);
+            xh[j] = f2((vo[u][j].x - sto[u].x) * sto[u].y, (vo[u][j].y - sto[u].x) * sto[u].y);
+            const float2 don = f2(lm.x * ds.x, lm.y * ds.y);
+            gg[j] = f2(don.x * gm.x, don.y * gm.y);
+            o1 += gg[j].x + gg[j].y;
+            o2 = fmaf(gg[j].x, xh[j].x, fmaf(gg[j].y, xh[j].y, o2));
+            sgo[j] = f2(fmaf(don.x, xh[j].x, sgo[j].x), fmaf(don.y, xh[j].y, sgo[j].y));
+            sbo[j] = f2(sbo[j].x + don.x, sbo[j].y + don.y);
+            slm[j] = f2(fmaf(ds.x, xh[j].x * gm.x + bt.x, slm[j].x), fmaf(ds.y, xh[j].y * gm.y + bt.y, slm[j].y));
+          }
+        o1 = warp_sum(o1) * invC;
+        o2 = warp_sum(o2) * invC;
+#pragma unroll
+        for (int j = 0; j < kDeitMaxCJ; ++j)
+          if (j < CJ) {
+            const int cc = 2 * (j * 32 + lane);
+            stg_pair<T>(dob + (int64_t)t * C + cc, f2(sto[u].y * (gg[j].x - o1 - xh[j].x * o2), sto[u].y * (gg[j].y - o1 - xh[j].y * o2)));
+          }
       }
     }
   }

@@ -19,12 +19,11 @@ static bool deit_plan(const MrlaDeitArgs* a, DeitPlan* p) {
   if (a->dtype < MRLA_F32 || a->dtype > MRLA_F16) return false;
   const size_t es = a->dtype == MRLA_F32 ? 4 : 2;
   p->NQ = (a->S + kV7 - 1) / kV7;
-  p->threads = p->NQ * a->C / 2;
-  if (p->threads > 384) return false;
-  if (p->threads < 64) p->threads = 64;
+  if (p->NQ * a->C / 2 > 384) return false;
+  p->threads = (p->NQ * a->C / 2 <= 192) ? 192 : 384;   // the image march uses the first NQ*C/2 threads
   p->nw = p->threads / 32;
   const size_t tile = (size_t)a->n * a->C * es;
-  p->smem_fwd = tile + ((size_t)2 * a->C + 64) * sizeof(float) + (size_t)a->n * sizeof(float2);
+  p->smem_fwd = tile + ((size_t)2 * a->C + 64 + (size_t)p->nw * a->C) * sizeof(float) + (size_t)a->n * sizeof(float2);
   size_t red = (size_t)p->NQ * 10 * a->C;
   if ((size_t)p->nw * 5 * a->C > red) red = (size_t)p->nw * 5 * a->C;
   p->smem_bwd = tile + ((size_t)6 * a->C + 128 + red) * sizeof(float);
@@ -45,10 +44,18 @@ template <typename T>
 static int deit_forward_t(const MrlaDeitArgs& a, const DeitPlan& p, cudaStream_t st) {
   DeitParams P;
   deit_fill(&P, a, p);
-  auto k = k_deit_light_fwd<T>;
-  cudaError_t e = ensure_smem_once(k, p.smem_fwd);
-  if (e != cudaSuccess) return (int)e;
-  k<<<a.B, p.threads, p.smem_fwd, st>>>(P);
+  cudaError_t e;
+  if (p.threads == 192) {
+    auto k = k_deit_light_fwd<T, 192>;
+    e = ensure_smem_once(k, p.smem_fwd);
+    if (e != cudaSuccess) return (int)e;
+    k<<<a.B, p.threads, p.smem_fwd, st>>>(P);
+  } else {
+    auto k = k_deit_light_fwd<T, 384>;
+    e = ensure_smem_once(k, p.smem_fwd);
+    if (e != cudaSuccess) return (int)e;
+    k<<<a.B, p.threads, p.smem_fwd, st>>>(P);
+  }
   MRLA_V7_CHECK();
   return MRLA_OK;
 }
@@ -57,10 +64,18 @@ template <typename T>
 static int deit_backward_t(const MrlaDeitArgs& a, const DeitPlan& p, cudaStream_t st) {
   DeitParams P;
   deit_fill(&P, a, p);
-  auto k = k_deit_light_bwd<T>;
-  cudaError_t e = ensure_smem_once(k, p.smem_bwd);
-  if (e != cudaSuccess) return (int)e;
-  k<<<a.B, p.threads, p.smem_bwd, st>>>(P);
+  cudaError_t e;
+  if (p.threads == 192) {
+    auto k = k_deit_light_bwd<T, 192>;
+    e = ensure_smem_once(k, p.smem_bwd);
+    if (e != cudaSuccess) return (int)e;
+    k<<<a.B, p.threads, p.smem_bwd, st>>>(P);
+  } else {
+    auto k = k_deit_light_bwd<T, 384>;
+    e = ensure_smem_once(k, p.smem_bwd);
+    if (e != cudaSuccess) return (int)e;
+    k<<<a.B, p.threads, p.smem_bwd, st>>>(P);
+  }
   MRLA_V7_CHECK();
   k_deit_reduce<<<(P.PW + 255) / 256, 256, 0, st>>>(a.scratch, a.B, P.PW, a.dparams);
   MRLA_V7_CHECK();
