@@ -305,6 +305,27 @@ size_t mrla_deit_light_scratch_bytes(const MrlaDeitArgs* a);
 int mrla_deit_light_forward(const MrlaDeitArgs* a, void* stream);
 int mrla_deit_light_backward(const MrlaDeitArgs* a, void* stream);
 
+/* Token LayerNorm over the last dimension of a dense [B, n, C] tensor (one warp per token), used by the DeiT MRLA-base module
+ * (deit/deit_mrla_base.py:224-229, 242): forward also copies the normalised cls row (t = 0) to `cls_out[b*bs_cls + c]` (the
+ * module output's row 0), backward takes d(xn) of token 0 from `g_cls` and of tokens t >= 1 from `g_img[b*bs_gimg + (t-1)*C + c]`
+ * (the tail's image gradient), so neither torch.cat nor a gradient scatter is needed.  Replaces at::layer_norm (+ backward).
+ * C even, C <= 768; dparams [2,C] = d(gamma), d(beta); scratch from mrla_layernorm_scratch_bytes(). */
+typedef struct MrlaLnArgs {
+  int32_t B, n, C, dtype;
+  float eps, reserved0;
+  const void* x; void* xn; void* cls_out; int64_t bs_cls;
+  const float* gamma; const float* beta;
+  float* stats;            /* [B,n,2] mean, rstd (saved) */
+  const void* g_cls; int64_t bs_gcls; const void* g_img; int64_t bs_gimg;
+  void* dx;
+  float* dparams;          /* [2,C] */
+  float* scratch; size_t scratch_bytes;
+} MrlaLnArgs;
+size_t mrla_sizeof_ln_args(void);
+size_t mrla_layernorm_scratch_bytes(const MrlaLnArgs* a);
+int mrla_layernorm_forward(const MrlaLnArgs* a, void* stream);
+int mrla_layernorm_backward(const MrlaLnArgs* a, void* stream);
+
 /* Number of kernel launches the last forward / backward call on this thread enqueued
  * (bench.py reports it as gpu_launches). */
 int mrla_last_launch_count(void);

@@ -80,6 +80,14 @@ class MrlaDeitArgs(ctypes.Structure):
     )
 
 
+class MrlaLnArgs(ctypes.Structure):
+    """Mirror of `struct MrlaLnArgs` (include/mrla_b200.h)."""
+    _fields_ = ([(n, _i32) for n in ("B", "n", "C", "dtype")] + [("eps", _f32), ("reserved0", _f32)]
+                + [("x", _vp), ("xn", _vp), ("cls_out", _vp), ("bs_cls", _i64), ("gamma", _vp), ("beta", _vp), ("stats", _vp),
+                   ("g_cls", _vp), ("bs_gcls", _i64), ("g_img", _vp), ("bs_gimg", _i64), ("dx", _vp), ("dparams", _vp),
+                   ("scratch", _vp), ("scratch_bytes", ctypes.c_size_t)])
+
+
 _lib = None
 _lock = threading.Lock()
 
@@ -91,6 +99,7 @@ EXPORTS = (
     "mrla_sizeof_bn_args", "mrla_bn_scratch_bytes", "mrla_bn_forward", "mrla_bn_backward",
     "mrla_sizeof_deit_args", "mrla_deit_light_supported", "mrla_deit_light_scratch_bytes", "mrla_deit_light_forward",
     "mrla_deit_light_backward",
+    "mrla_sizeof_ln_args", "mrla_layernorm_scratch_bytes", "mrla_layernorm_forward", "mrla_layernorm_backward",
 )
 
 
@@ -156,6 +165,15 @@ def lib() -> ctypes.CDLL:
             f = getattr(L, f"mrla_deit_light_{d}")
             f.restype = ctypes.c_int
             f.argtypes = [ctypes.POINTER(MrlaDeitArgs), ctypes.c_void_p]
+        L.mrla_sizeof_ln_args.restype = ctypes.c_size_t
+        if L.mrla_sizeof_ln_args() != ctypes.sizeof(MrlaLnArgs):
+            raise RuntimeError("MrlaLnArgs layout mismatch between _lib.py and include/mrla_b200.h")
+        L.mrla_layernorm_scratch_bytes.restype = ctypes.c_size_t
+        L.mrla_layernorm_scratch_bytes.argtypes = [ctypes.POINTER(MrlaLnArgs)]
+        for d in ("forward", "backward"):
+            f = getattr(L, f"mrla_layernorm_{d}")
+            f.restype = ctypes.c_int
+            f.argtypes = [ctypes.POINTER(MrlaLnArgs), ctypes.c_void_p]
         for name, st in (("light", MrlaLightArgs), ("base", MrlaBaseArgs)):
             f = getattr(L, f"mrla_{name}_bwd_scratch_bytes")
             f.restype = ctypes.c_size_t

@@ -603,4 +603,118 @@ static __global__ void k_deit_reduce(const float* __restrict__ part, int B, int 
   out[i] = s;
 }
 
+
+// =====================================================================================================
+// Token LayerNorm (one warp per token) for the modules that keep the generic tail kernels: DeiT MRLA-base
+// (deit/deit_mrla_base.py:224-229 `xn = self.normx(xt)`), replacing at::layer_norm and its backward.
+//   forward : xn[b,t,:] = (x - mean) * rstd * gamma + beta ; stats [B,n,2] ; the cls row (t = 0) is ALSO written to
+//             cls_out[b, 0, :] (the module's output buffer: out[:, 0] = xn[:, 0], :242), so no torch.cat is needed.
+//   backward: d(xn) of token 0 comes from g_cls[b, 0, :], of token t >= 1 from g_img[b, t-1, :] (the gradient of the
+//             token image as the tail's backward left it) -> dx ; per-CTA partial sums of d(gamma), d(beta).
+// =====================================================================================================
+struct LnParams {
+  int B, n, C;
+  float eps;
+  const void* x; void* xn; void* cls_out; int64_t bs_cls;    // bs_* = batch strides in elements
+  const float* gamma; const float* beta;
+  float* stats;
+  const void* g_cls; int64_t bs_gcls; const void* g_img; int64_t bs_gimg;
+  void* dx; float* part;                                       // part [gridDim.x, 2, C]
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_ln_tokens_fwd(const LnParams P) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int64_t ntok = (int64_t)P.B * P.n;
+  for (int64_t tok = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); tok < ntok; tok += (int64_t)gridDim.x * wpb) {
+    const T* xr = static_cast<const T*>(P.x) + tok * P.C;
+    float s = 0.f;
+    for (int c = 2 * lane; c < P.C; c += 64) { const float2 v = ldg_pair<T>(xr + c); s += v.x + v.y; }
+    const float mean = warp_sum(s) / (float)P.C;
+    float q = 0.f;
+    for (int c = 2 * lane; c < P.C; c += 64) {
+      const float2 v = ldg_pair<T>(xr + c);
+      q = fmaf(v.x - mean, v.x - mean, fmaf(v.y - mean, v.y - mean, q));
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)P.C + P.eps);
+    const int64_t b = tok / P.n;
+    const int t = (int)(tok - b * P.n);
+    T* yr = static_cast<T*>(P.xn) + tok * P.C;
+    T* cr = (t == 0 && P.cls_out) ? static_cast<T*>(P.cls_out) + b * P.bs_cls : nullptr;
+    for (int c = 2 * lane; c < P.C; c += 64) {
+      const float2 v = ldg_pair<T>(xr + c);
+      const float2 gm = *reinterpret_cast<const float2*>(P.gamma + c), bt = *reinterpret_cast<const float2*>(P.beta + c);
+      const float2 y = f2((v.x - mean) * rstd * gm.x + bt.x, (v.y - mean) * rstd * gm.y + bt.y);
+      stg_pair<T>(yr + c, y);
+      if (cr) stg_pair<T>(cr + c, y);
+    }
+    if (lane == 0) *reinterpret_cast<float2*>(P.stats + tok * 2) = f2(mean, rstd);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_ln_tokens_bwd(const LnParams P) {
+  extern __shared__ float sm[];   // [2][C] per-CTA sums (shared-memory atomics would be non-deterministic: warps take turns)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < 2 * P.C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int64_t ntok = (int64_t)P.B * P.n;
+  const float invC = 1.f / (float)P.C;
+  // every warp keeps its own channel sums in registers for up to 768 channels (12 pairs per lane)
+  float2 sg[12], sb[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) sg[j] = sb[j] = f2(0.f, 0.f);
+  for (int64_t tok = (int64_t)blockIdx.x * wpb + warp; tok < ntok; tok += (int64_t)gridDim.x * wpb) {
+    const int64_t b = tok / P.n;
+    const int t = (int)(tok - b * P.n);
+    const T* xr = static_cast<const T*>(P.x) + tok * P.C;
+    const T* gr = (t == 0) ? static_cast<const T*>(P.g_cls) + b * P.bs_gcls
+                           : static_cast<const T*>(P.g_img) + b * P.bs_gimg + (int64_t)(t - 1) * P.C;
+    const float2 st = *reinterpret_cast<const float2*>(P.stats + tok * 2);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+      const int c = 2 * lane + 64 * j;
+      if (c < P.C) {
+        const float2 v = ldg_pair<T>(xr + c), g = ldg_pair<T>(gr + c);
+        const float2 gm = *reinterpret_cast<const float2*>(P.gamma + c);
+        const float2 xh = f2((v.x - st.x) * st.y, (v.y - st.x) * st.y);
+        const float2 gg = f2(g.x * gm.x, g.y * gm.y);
+        s1 += gg.x + gg.y;
+        s2 = fmaf(gg.x, xh.x, fmaf(gg.y, xh.y, s2));
+        sg[j] = f2(fmaf(g.x, xh.x, sg[j].x), fmaf(g.y, xh.y, sg[j].y));
+        sb[j] = f2(sb[j].x + g.x, sb[j].y + g.y);
+      }
+    }
+    s1 = warp_sum(s1) * invC;
+    s2 = warp_sum(s2) * invC;
+    T* dr = static_cast<T*>(P.dx) + tok * P.C;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+      const int c = 2 * lane + 64 * j;
+      if (c < P.C) {
+        const float2 v = ldg_pair<T>(xr + c), g = ldg_pair<T>(gr + c);
+        const float2 gm = *reinterpret_cast<const float2*>(P.gamma + c);
+        const float2 xh = f2((v.x - st.x) * st.y, (v.y - st.x) * st.y);
+        stg_pair<T>(dr + c, f2(st.y * (g.x * gm.x - s1 - xh.x * s2), st.y * (g.y * gm.y - s1 - xh.y * s2)));
+      }
+    }
+  }
+  // deterministic CTA reduction: warps add their sums one after the other
+  for (int w = 0; w < wpb; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int j = 0; j < 12; ++j) {
+        const int c = 2 * lane + 64 * j;
+        if (c < P.C) {
+          sm[c] += sg[j].x; sm[c + 1] += sg[j].y;
+          sm[P.C + c] += sb[j].x; sm[P.C + c + 1] += sb[j].y;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < 2 * P.C; i += blockDim.x) P.part[(int64_t)blockIdx.x * 2 * P.C + i] = sm[i];
+}
+
 }  // namespace mrla

