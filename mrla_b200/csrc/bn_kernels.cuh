@@ -62,7 +62,20 @@ __global__ void __launch_bounds__(256) k_bn_stats(const T* __restrict__ x, float
     }
     const int64_t stride = (int64_t)gridDim.x * s.RL;
     int64_t row = (int64_t)blockIdx.x * s.RL + rl;
-    for (; row + stride < s.M; row += 2 * stride) {   // two independent 128-bit loads in flight
+    for (; row + 3 * stride < s.M; row += 4 * stride) {   // four independent 128-bit loads in flight
+      float a[kSV], b[kSV], e[kSV], f[kSV];
+      Vec8<T>::ld(x + row * s.C + c, a);
+      Vec8<T>::ld(x + (row + stride) * s.C + c, b);
+      Vec8<T>::ld(x + (row + 2 * stride) * s.C + c, e);
+      Vec8<T>::ld(x + (row + 3 * stride) * s.C + c, f);
+#pragma unroll
+      for (int i = 0; i < kSV; ++i) {
+        const float da = a[i] - pv[i], db = b[i] - pv[i], de = e[i] - pv[i], df = f[i] - pv[i];
+        acc[i] += (da + db) + (de + df);
+        acc[kSV + i] = fmaf(da, da, fmaf(db, db, fmaf(de, de, fmaf(df, df, acc[kSV + i]))));
+      }
+    }
+    for (; row + stride < s.M; row += 2 * stride) {
       float a[kSV], b[kSV];
       Vec8<T>::ld(x + row * s.C + c, a);
       Vec8<T>::ld(x + (row + stride) * s.C + c, b);

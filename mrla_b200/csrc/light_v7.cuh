@@ -31,6 +31,7 @@ constexpr int kV7 = 7;   // output columns per consumer thread
 struct V7Params {
   int B, C, H, W;
   int NQ, ncb, S, cpc;     // column groups, channel blocks, pipeline stages, CTAs per channel block (grid = ncb*cpc)
+  int NT;                  // column tiles of NQ*7 columns per image (W > 56: mmdet feature maps); 1 otherwise
   int rev;                 // 1: walk the batch from the last sample down (the previous sweep left that end in L2)
   int ncw;                 // consumer warps per CTA
   int hint;                // L2 policy of the tile loads: 0 default, 1 evict_first
@@ -122,21 +123,24 @@ __device__ __forceinline__ void v7_producer(const CUtensorMap* tm0, const CUtens
   uint32_t ph = 1;   // first pass over the ring: slots are free
   for (int bi = m; bi < P.B; bi += P.cpc) {
     const int b = P.rev ? P.B - 1 - bi : bi;
-    for (int r = 0; r < P.H; ++r) {
-      mbar_wait_s(bar_s + 128 + st * 8, ph);
-      const uint32_t fb = bar_s + st * 8;
-      const uint32_t dst = stages_s + (uint32_t)st * P.stage_bytes;
-      mbar_expect_tx_s(fb, P.stage_bytes);
-      if (P.hint) {
-        tma_load_4d_hint(dst, tm0, fb, cb * CB, w0, r, b, pol);
-        if (NT > 1) tma_load_4d_hint(dst + P.x_bytes, tm1, fb, cb * CB, w1, r, b, pol);
-        if (NT > 2) tma_load_4d_hint(dst + P.x_bytes + P.o_bytes, tm2, fb, cb * CB, w2, r, b, pol);
-      } else {
-        tma_load_4d_s(dst, tm0, fb, cb * CB, w0, r, b);
-        if (NT > 1) tma_load_4d_s(dst + P.x_bytes, tm1, fb, cb * CB, w1, r, b);
-        if (NT > 2) tma_load_4d_s(dst + P.x_bytes + P.o_bytes, tm2, fb, cb * CB, w2, r, b);
+    for (int tile = 0; tile < P.NT; ++tile) {
+      const int t0 = tile * P.NQ * kV7;   // first image column of the tile
+      for (int r = 0; r < P.H; ++r) {
+        mbar_wait_s(bar_s + 128 + st * 8, ph);
+        const uint32_t fb = bar_s + st * 8;
+        const uint32_t dst = stages_s + (uint32_t)st * P.stage_bytes;
+        mbar_expect_tx_s(fb, P.stage_bytes);
+        if (P.hint) {
+          tma_load_4d_hint(dst, tm0, fb, cb * CB, t0 + w0, r, b, pol);
+          if (NT > 1) tma_load_4d_hint(dst + P.x_bytes, tm1, fb, cb * CB, t0 + w1, r, b, pol);
+          if (NT > 2) tma_load_4d_hint(dst + P.x_bytes + P.o_bytes, tm2, fb, cb * CB, t0 + w2, r, b, pol);
+        } else {
+          tma_load_4d_s(dst, tm0, fb, cb * CB, t0 + w0, r, b);
+          if (NT > 1) tma_load_4d_s(dst + P.x_bytes, tm1, fb, cb * CB, t0 + w1, r, b);
+          if (NT > 2) tma_load_4d_s(dst + P.x_bytes + P.o_bytes, tm2, fb, cb * CB, t0 + w2, r, b);
+        }
+        if (++st == P.S) { st = 0; ph ^= 1; }
       }
-      if (++st == P.S) { st = 0; ph ^= 1; }
     }
   }
 }
@@ -174,6 +178,18 @@ struct V7Fwd {
   __device__ __forceinline__ V7Fwd(const V7Params& P_) : P(P_) {}
 
   __device__ __forceinline__ bool col_ok(int j) const { return (vmask >> j) & 1u; }
+  // column tile starting at image column t0: validity of this thread's window columns, TMA store column
+  __device__ __forceinline__ void set_tile(int t0, int q) {
+    vmask = 0;
+#pragma unroll
+    for (int j = 0; j < KW; ++j) {
+      const int col = t0 + q * K - 1 + j;
+      if (col >= 0 && col < P.W) vmask |= 1u << j;
+    }
+    em0 = col_ok(0) ? 0xffffffffu : 0u;
+    em1 = col_ok(KW - 1) ? 0xffffffffu : 0u;
+    ycol = t0 + q * K;
+  }
 
   template <int I, bool FETCH, bool OUT>
   __device__ __forceinline__ void step() {
@@ -349,16 +365,8 @@ k_v7_fwd(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUten
   S.lane = threadIdx.x & 31;
   S.tbase = (uint32_t)(q * K) * F::CS + (uint32_t)p * 2 * ES;
   S.obuf = smem_u32(tail) + (uint32_t)warp * (2 * K * F::OW) + (uint32_t)S.lane * 2 * ES;
-  S.ycol = q * K;
   S.ychan = cb * CB + ((warp * 32) % NP) * 2;
-  S.vmask = 0;
-#pragma unroll
-  for (int j = 0; j < F::KW; ++j) {
-    const int col = q * K - 1 + j;
-    if (col >= 0 && col < P.W) S.vmask |= 1u << j;
-  }
-  S.em0 = S.col_ok(0) ? 0xffffffffu : 0u;
-  S.em1 = S.col_ok(F::KW - 1) ? 0xffffffffu : 0u;
+  S.set_tile(0, q);
   S.st = 0;
   S.ph = 0;
   S.ob = 0;
@@ -384,7 +392,14 @@ k_v7_fwd(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUten
     }
 #pragma unroll
     for (int i = 0; i < (F::NACC > 0 ? F::NACC : 1); ++i) { S.acc[i] = f2(0.f, 0.f); S.accb[i] = f2(0.f, 0.f); }
-    S.image();
+    if (P.NT == 1) {
+      S.image();
+    } else {
+      for (int tile = 0; tile < P.NT; ++tile) {   // W > 56: column tiles; the moments run over all of them
+        S.set_tile(tile * P.NQ * K, q);
+        S.image();
+      }
+    }
     if (F::NACC > 0) {
       if (P.NQ == 1) {
 #pragma unroll
@@ -469,15 +484,34 @@ struct V7Bwd {
   __device__ __forceinline__ bool col_ok(int j) const { return (vmask >> j) & 1u; }
   // request global row g (of this CTA's row sequence) into stage sx
   __device__ __forceinline__ void issue_row(int g, int sx) {
-    const int img = g / P.H, row = g - img * P.H;
+    const int per_img = P.NT * P.H;
+    const int img = g / per_img, rem = g - img * per_img;
+    const int tile = rem / P.H, row = rem - tile * P.H;
+    const int t0 = tile * P.NQ * K;
     const int bi = m + img * P.cpc;
     const int bb = P.rev ? P.B - 1 - bi : bi;
     const uint32_t fb = bar_s + sx * 8;
     const uint32_t dst = stages_s + (uint32_t)sx * P.stage_bytes;
     mbar_expect_tx_s(fb, P.stage_bytes);
-    tma_load_4d_hint(dst, tm_x, fb, cb * CB, -2, row, bb, pol);
-    tma_load_4d_hint(dst + P.x_bytes, tm_o, fb, cb * CB, XF ? -2 : -1, row, bb, pol);
-    tma_load_4d_hint(dst + P.x_bytes + P.o_bytes, tm_dy, fb, cb * CB, -1, row, bb, pol);
+    tma_load_4d_hint(dst, tm_x, fb, cb * CB, t0 - 2, row, bb, pol);
+    tma_load_4d_hint(dst + P.x_bytes, tm_o, fb, cb * CB, t0 + (XF ? -2 : -1), row, bb, pol);
+    tma_load_4d_hint(dst + P.x_bytes + P.o_bytes, tm_dy, fb, cb * CB, t0 - 1, row, bb, pol);
+  }
+  // column tile starting at image column t0: validity of the x-window / T columns, TMA store column
+  __device__ __forceinline__ void set_tile(int t0, int q) {
+    vmask = 0;
+#pragma unroll
+    for (int j = 0; j < KX; ++j) {
+      const int col = t0 + q * K - 2 + j;
+      if (col >= 0 && col < P.W) vmask |= 1u << j;
+    }
+    em[0] = col_ok(0) ? 0xffffffffu : 0u;
+    em[1] = col_ok(1) ? 0xffffffffu : 0u;
+    em[2] = col_ok(KX - 2) ? 0xffffffffu : 0u;
+    em[3] = col_ok(KX - 1) ? 0xffffffffu : 0u;
+    tm0 = col_ok(1) ? f2(1.f, 1.f) : f2(0.f, 0.f);
+    tm1 = col_ok(KX - 2) ? f2(1.f, 1.f) : f2(0.f, 0.f);
+    ycol = t0 + q * K;
   }
   // this warp is done with stage sx, which held global row g
   __device__ __forceinline__ void release(int sx, int g) {
@@ -714,7 +748,7 @@ k_v7_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUten
   S.lane = threadIdx.x & 31;
   S.cb = cb;
   S.m = m;
-  S.rows_total = n_my * P.H;
+  S.rows_total = n_my * P.NT * P.H;
   S.grow = 0;
   S.gidx[0] = S.gidx[1] = S.gidx[2] = 0;
   S.cnt_s = bar_s + 128;   // the release counters live where the forward kernels keep their empty barriers
@@ -736,20 +770,8 @@ k_v7_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUten
     for (int s = 0; s < P.S && s < S.rows_total; ++s) S.issue_row(s, s);   // fill the pipeline
   S.tbase = (uint32_t)(q * K) * Bk::CS + (uint32_t)p * 2 * ES;
   S.obuf = smem_u32(tail) + (uint32_t)warp * (3 * 2 * Bk::OROW) + (uint32_t)S.lane * 2 * ES;
-  S.ycol = q * K;
   S.ychan = cb * CB + ((warp * 32) % NP) * 2;
-  S.vmask = 0;
-#pragma unroll
-  for (int j = 0; j < Bk::KX; ++j) {
-    const int col = q * K - 2 + j;
-    if (col >= 0 && col < P.W) S.vmask |= 1u << j;
-  }
-  S.em[0] = S.col_ok(0) ? 0xffffffffu : 0u;
-  S.em[1] = S.col_ok(1) ? 0xffffffffu : 0u;
-  S.em[2] = S.col_ok(Bk::KX - 2) ? 0xffffffffu : 0u;
-  S.em[3] = S.col_ok(Bk::KX - 1) ? 0xffffffffu : 0u;
-  S.tm0 = S.col_ok(1) ? f2(1.f, 1.f) : f2(0.f, 0.f);
-  S.tm1 = S.col_ok(Bk::KX - 2) ? f2(1.f, 1.f) : f2(0.f, 0.f);
+  S.set_tile(0, q);
   S.st = 0;
   S.ph = 0;
   S.sidx[0] = S.sidx[1] = S.sidx[2] = 0;
@@ -777,7 +799,14 @@ k_v7_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUten
     S.q3 = *reinterpret_cast<const float2*>(cp + 3 * BC);
     S.ta = *reinterpret_cast<const float2*>(cp + 4 * BC);
     S.dyc = *reinterpret_cast<const float2*>(cp + 5 * BC);
-    S.image();
+    if (P.NT == 1) {
+      S.image();
+    } else {
+      for (int tile = 0; tile < P.NT; ++tile) {
+        S.set_tile(tile * P.NQ * K, q);
+        S.image();
+      }
+    }
   }
   if (S.lane == 0) bulk_wait_all<0>();
   // per-CTA partials of dWv (and the bn3 sums): reduce over the NQ column groups; the scratch aliases the pipeline

@@ -76,7 +76,7 @@ inline cudaError_t ensure_smem_once(Kern kernel, size_t bytes) {
 enum { V7_S1 = 0, V7_S2 = 1, V7_SA = 2, V7_SB = 3 };
 
 struct V7Plan {
-  int CB, NQ, S, ncb, cpc, grid, ncw, threads, ctas;
+  int CB, NQ, NT, S, ncb, cpc, grid, ncw, threads, ctas;
   int xcols, ocols, dycols;
   uint32_t x_bytes, o_bytes, dy_bytes, stage_bytes;
   size_t smem;
@@ -90,9 +90,12 @@ inline bool v7_ptr_ok(const void* ptr, int64_t bs, int es) {
 // shape-level eligibility + resources of one sweep; xf = x is re-formed from (z, z_coef, o)
 inline bool v7_plan(const MrlaLightArgs& a, int kind, bool xf, V7Plan* p) {
   if (a.layout != MRLA_NHWC || a.o == nullptr || a.act != MRLA_ACT_NONE) return false;
-  if (a.C % 64 || a.H < 3 || a.W < 1 || a.W > 8 * kV7) return false;
+  if (a.C % 64 || a.H < 3 || a.W < 1 || a.W > 512) return false;   // 512: the width limit of the generic plan
   const int es = a.dtype == MRLA_F32 ? 4 : 2;
-  const int NQ = (a.W + kV7 - 1) / kV7;
+  // W > 56 (mmdet feature maps): column tiles of 8 groups of 7 columns; halo columns of a tile are real data of its
+  // neighbours (the TMA box simply starts one / two columns to the left), only image borders are masked
+  const int NQ = a.W > 8 * kV7 ? 8 : (a.W + kV7 - 1) / kV7;
+  p->NT = (a.W + NQ * kV7 - 1) / (NQ * kV7);
   int CB = 0;
   for (int cb : {256, 128, 64})
     if (a.C % cb == 0 && NQ * cb / 2 <= 256) { CB = cb; break; }
@@ -134,7 +137,7 @@ inline bool v7_plan(const MrlaLightArgs& a, int kind, bool xf, V7Plan* p) {
   if (cpc > a.B) cpc = a.B;
   p->cpc = cpc;
   p->grid = p->ncb * cpc;
-  p->ragged = (a.W % kV7) != 0;
+  p->ragged = (a.W % kV7) != 0 || p->NT > 1;
   return true;
 }
 
@@ -149,7 +152,7 @@ inline bool v7_virtual_x_ok(const MrlaLightArgs& a) {
 
 inline void v7_fill(V7Params* P, const MrlaLightArgs& a, const V7Plan& p) {
   P->B = a.B; P->C = a.C; P->H = a.H; P->W = a.W;
-  P->NQ = p.NQ; P->ncb = p.ncb; P->S = p.S; P->cpc = p.cpc; P->rev = 0; P->ncw = p.ncw; P->hint = 0;
+  P->NQ = p.NQ; P->NT = p.NT; P->ncb = p.ncb; P->S = p.S; P->cpc = p.cpc; P->rev = 0; P->ncw = p.ncw; P->hint = 0;
   P->x_bytes = p.x_bytes; P->o_bytes = p.o_bytes; P->dy_bytes = p.dy_bytes; P->stage_bytes = p.stage_bytes;
   P->xo_cols = 0;
   P->wv = a.wv; P->zcoef = a.z_coef; P->coef = a.coef; P->mom = nullptr; P->res = a.residual ? 1.f : 0.f;

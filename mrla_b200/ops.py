@@ -512,7 +512,9 @@ def bn3_tail_eligible(c3: torch.Tensor, o: torch.Tensor, bn3: "torch.nn.BatchNor
     a.dtype, a.layout, a.act, a.bn_mode = _DTYPES[c3.dtype], _lib.NHWC, cfg.act, cfg.bn_mode
     a.bs_x = a.bs_o = a.bs_y = a.bs_z = n
     a.x, a.o, a.z = _ptr(c3), _ptr(o), _ptr(c3)   # x / y buffers are fresh allocations with the same alignment
-    return bool(_lib.lib().mrla_light_fwd_folds_bn(ctypes.byref(a)))
+    L = _lib.lib()
+    # the round-1 materialising kernels (W <= 56), or the v7 sweeps that never materialise x (column-tiled, W <= 512)
+    return bool(L.mrla_light_fwd_folds_bn(ctypes.byref(a))) or (ALLOW_VIRTUAL_X and bool(L.mrla_light_virtual_x(ctypes.byref(a))))
 
 
 def bn3_light_tail(c3: torch.Tensor, o: torch.Tensor, bn3: "torch.nn.BatchNorm2d", wq, wk, wv, lam, gamma, beta,
@@ -818,7 +820,12 @@ class _BaseTail(torch.autograd.Function):
 def base_tail(x, prev_k, prev_v, wq, wk, wv, gamma=None, beta=None, running_mean=None, running_var=None,
               drop_scale=None, *, init_cell: bool, cfg: BaseCfg, cap_hint: int = 8, out=None):
     """Fused MRLA-base tail.  Returns (y, K, V) with K [B,t,C] / V [B,t,C,H,W] views of the in-place stage cache
-    (reference signature: mrla_base_module.py:54-89 `forward(x, prev_K, prev_V) -> (out, K, V)`)."""
+    (reference signature: mrla_base_module.py:54-89 `forward(x, prev_K, prev_V) -> (out, K, V)`).
+
+    K and V are handles for the NEXT block of the stage: their gradients flow through the stage cache (dV / dK are
+    accumulated in place by the later blocks and consumed by the block that produced the slot), not through an autograd
+    edge of these views.  Feeding K / V to anything other than the next `base_tail` of the same stage (an auxiliary loss
+    on the keys, say) gets no gradient — the reference's `torch.cat` results would; no MRLA model does that."""
     _require_cuda(x, "x")
     x_c, layout, _ = _canon(x)
     if layout == _lib.NCHW and out is None and _want_nhwc(x_c):

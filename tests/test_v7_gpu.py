@@ -37,9 +37,10 @@ def _bn3_tail_case(B, C, HW, dtype, dev, seed=0, drop=True):
     from mrla_b200.modules.mrla_light_module import eca_kernel_size
     g = torch.Generator(device=dev).manual_seed(seed)
     rn = lambda *s: torch.randn(*s, device=dev, generator=g)
-    c3 = _cl(rn(B, C, HW, HW).to(dtype))
-    idt = _cl(torch.relu(rn(B, C, HW, HW)).to(dtype))
-    dy = _cl(rn(B, C, HW, HW).to(dtype))
+    H, W = HW if isinstance(HW, tuple) else (HW, HW)
+    c3 = _cl(rn(B, C, H, W).to(dtype))
+    idt = _cl(torch.relu(rn(B, C, H, W)).to(dtype))
+    dy = _cl(rn(B, C, H, W).to(dtype))
     k = eca_kernel_size(C)
     P = dict(w3=0.5 + torch.rand(C, device=dev, generator=g), b3=0.3 * rn(C), wq=0.5 * rn(k), wk=0.5 * rn(k),
              wv=rn(C, 1, 3, 3) * (2 / 9) ** 0.5, lam=rn(C, 1, 1), gamma=1 + 0.3 * rn(C), beta=0.2 * rn(C))
@@ -121,6 +122,27 @@ def test_bn3_tail_virtual_x_vs_oracle(C, HW, dtype, B, cuda_device):
     torch.cuda.empty_cache()
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 20, 100), (3, 128, 9, 57), (1, 256, 200, 304), (2, 512, 100, 152)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_bn3_tail_virtual_x_wide_maps_vs_oracle(shape, dtype, cuda_device):
+    """W > 56 (the detection backbone's feature maps, mmdetection/.../resnet_mrlal.py: 200x304 at stage 1 for an 800x1216
+    image): the v7 sweeps walk each image in column tiles of 56; tile halos are the neighbouring tile's real columns."""
+    B, C, H, W = shape
+    dev = cuda_device
+    c3, idt, dy, P, ds, k = _bn3_tail_case(B, C, (H, W), dtype, dev, seed=C + W, drop=False)
+    y, dc3, did, grads, bufs = _run_product(c3, idt, dy, P, ds, k)
+    yr, dc3r, didr, gr, ex = _run_oracle(c3, idt, dy, P, ds, storage_dtype=None if dtype == torch.float32 else dtype)
+    tol = TOL[dtype]
+    assert rel_err(y, yr) < tol
+    eps_store = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -22
+    keep = (ex["pre"].abs() > eps_store * ex["z"].abs() + 1e-30)
+    assert keep.double().mean().item() > 0.99
+    assert _masked_rel_err(dc3, dc3r, keep) < tol
+    assert _masked_rel_err(did, didr, keep) < tol
+    for n in grads:
+        assert rel_err(grads[n], gr[n]) < 2 * tol, n
+
+
 @pytest.mark.parametrize("shape", [(8, 256, 56), (16, 512, 28), (32, 1024, 14), (32, 2048, 7), (4, 128, 9), (3, 64, 13)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32, torch.float16])
 def test_virtual_x_matches_materialised_x(shape, dtype, cuda_device, monkeypatch):
@@ -145,7 +167,7 @@ def test_virtual_x_matches_materialised_x(shape, dtype, cuda_device, monkeypatch
 
 
 @pytest.mark.parametrize("shape", [(4, 64, 7, 7), (3, 256, 9, 13), (2, 128, 56, 56), (5, 192, 14, 14), (2, 64, 3, 50),
-                                   (3, 512, 28, 28)])
+                                   (3, 512, 28, 28), (2, 64, 12, 100), (1, 128, 40, 84), (2, 192, 5, 57)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("mode", ["train", "eval", "none"])
 def test_plain_tail_on_v7_sweeps_vs_oracle(shape, dtype, mode, cuda_device):
