@@ -32,6 +32,8 @@ struct V7Params {
   int B, C, H, W;
   int NQ, ncb, S, cpc;     // column groups, channel blocks, pipeline stages, CTAs per channel block (grid = ncb*cpc)
   int NT;                  // column tiles of NQ*7 columns per image (W > 56: mmdet feature maps); 1 otherwise
+  int U, TPU;              // work units and column tiles per unit: (B, NT) = one unit per image, or (B*NT, 1) = one unit per
+                           // tile for small batches (the per-image moments are then accumulated with atomics)
   int rev;                 // 1: walk the batch from the last sample down (the previous sweep left that end in L2)
   int ncw;                 // consumer warps per CTA
   int hint;                // L2 policy of the tile loads: 0 default, 1 evict_first
@@ -121,9 +123,11 @@ __device__ __forceinline__ void v7_producer(const CUtensorMap* tm0, const CUtens
   const uint64_t pol = l2_policy_evict_first();
   int st = 0;
   uint32_t ph = 1;   // first pass over the ring: slots are free
-  for (int bi = m; bi < P.B; bi += P.cpc) {
+  const int NS = P.NT / P.TPU;   // units per image
+  for (int u = m; u < P.U; u += P.cpc) {
+    const int bi = u / NS, tile0 = (u - bi * NS) * P.TPU;
     const int b = P.rev ? P.B - 1 - bi : bi;
-    for (int tile = 0; tile < P.NT; ++tile) {
+    for (int tile = tile0; tile < tile0 + P.TPU; ++tile) {
       const int t0 = tile * P.NQ * kV7;   // first image column of the tile
       for (int r = 0; r < P.H; ++r) {
         mbar_wait_s(bar_s + 128 + st * 8, ph);
@@ -381,7 +385,9 @@ k_v7_fwd(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUten
   const int64_t BC = (int64_t)P.B * P.C;
   float2* red_base = reinterpret_cast<float2*>(tail);   // [2][NQ][NACC][NP]
   int red_sel = 0;
-  for (int bi = m; bi < P.B; bi += P.cpc) {
+  const int NS = P.NT / P.TPU;   // units per image
+  for (int u = m; u < P.U; u += P.cpc) {
+    const int bi = u / NS, tile0 = (u - bi * NS) * P.TPU;
     const int b = P.rev ? P.B - 1 - bi : bi;
     S.b = b;
     if (MODE == 1) {
@@ -395,7 +401,7 @@ k_v7_fwd(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUten
     if (P.NT == 1) {
       S.image();
     } else {
-      for (int tile = 0; tile < P.NT; ++tile) {   // W > 56: column tiles; the moments run over all of them
+      for (int tile = tile0; tile < tile0 + P.TPU; ++tile) {   // W > 56: column tiles; the moments run over all of them
         S.set_tile(tile * P.NQ * K, q);
         S.image();
       }
@@ -420,7 +426,13 @@ k_v7_fwd(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUten
             s.x += v.x;
             s.y += v.y;
           }
-          *reinterpret_cast<float2*>(P.mom + (int64_t)mi * BC + (int64_t)b * P.C + cb * CB + 2 * pp) = s;
+          float* dst = P.mom + (int64_t)mi * BC + (int64_t)b * P.C + cb * CB + 2 * pp;
+          if (NS == 1) {
+            *reinterpret_cast<float2*>(dst) = s;
+          } else {   // the image's tiles are spread over CTAs: the launcher zeroed `mom`
+            atomicAdd(dst, s.x);
+            atomicAdd(dst + 1, s.y);
+          }
         }
       }
     }
@@ -484,11 +496,12 @@ struct V7Bwd {
   __device__ __forceinline__ bool col_ok(int j) const { return (vmask >> j) & 1u; }
   // request global row g (of this CTA's row sequence) into stage sx
   __device__ __forceinline__ void issue_row(int g, int sx) {
-    const int per_img = P.NT * P.H;
-    const int img = g / per_img, rem = g - img * per_img;
-    const int tile = rem / P.H, row = rem - tile * P.H;
-    const int t0 = tile * P.NQ * K;
-    const int bi = m + img * P.cpc;
+    const int per_unit = P.TPU * P.H, NS = P.NT / P.TPU;
+    const int ui = g / per_unit, rem = g - ui * per_unit;
+    const int t = rem / P.H, row = rem - t * P.H;
+    const int u = m + ui * P.cpc;
+    const int bi = u / NS;
+    const int t0 = ((u - bi * NS) * P.TPU + t) * P.NQ * K;
     const int bb = P.rev ? P.B - 1 - bi : bi;
     const uint32_t fb = bar_s + sx * 8;
     const uint32_t dst = stages_s + (uint32_t)sx * P.stage_bytes;
@@ -732,7 +745,7 @@ k_v7_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUten
   unsigned char* stages = smem_raw + kV7Hdr;
   unsigned char* tail = stages + (size_t)P.S * P.stage_bytes;   // staging rows of all warps
   const int cb = blockIdx.x / P.cpc, m = blockIdx.x - cb * P.cpc;
-  const int n_my = (m < P.B) ? (P.B - 1 - m) / P.cpc + 1 : 0;
+  const int n_my = (m < P.U) ? (P.U - 1 - m) / P.cpc + 1 : 0;
   const uint32_t bar_s = smem_u32(smem_raw), stages_s = smem_u32(stages);
   const int ct = threadIdx.x;
   const int p = ct % NP, q = ct / NP;
@@ -748,7 +761,7 @@ k_v7_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUten
   S.lane = threadIdx.x & 31;
   S.cb = cb;
   S.m = m;
-  S.rows_total = n_my * P.NT * P.H;
+  S.rows_total = n_my * P.TPU * P.H;
   S.grow = 0;
   S.gidx[0] = S.gidx[1] = S.gidx[2] = 0;
   S.cnt_s = bar_s + 128;   // the release counters live where the forward kernels keep their empty barriers
@@ -789,7 +802,9 @@ k_v7_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUten
   }
   S.sdz = S.sdzc = f2(0.f, 0.f);
   const int64_t BC = (int64_t)P.B * P.C;
-  for (int bi = m; bi < P.B; bi += P.cpc) {
+  const int NS = P.NT / P.TPU;   // units per image
+  for (int u = m; u < P.U; u += P.cpc) {
+    const int bi = u / NS, tile0 = (u - bi * NS) * P.TPU;
     const int b = P.rev ? P.B - 1 - bi : bi;
     S.b = b;
     const float* cp = P.bcoef + (int64_t)b * P.C + c;
@@ -802,7 +817,7 @@ k_v7_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUten
     if (P.NT == 1) {
       S.image();
     } else {
-      for (int tile = 0; tile < P.NT; ++tile) {
+      for (int tile = tile0; tile < tile0 + P.TPU; ++tile) {
         S.set_tile(tile * P.NQ * K, q);
         S.image();
       }

@@ -76,7 +76,7 @@ inline cudaError_t ensure_smem_once(Kern kernel, size_t bytes) {
 enum { V7_S1 = 0, V7_S2 = 1, V7_SA = 2, V7_SB = 3 };
 
 struct V7Plan {
-  int CB, NQ, NT, S, ncb, cpc, grid, ncw, threads, ctas;
+  int CB, NQ, NT, U, TPU, S, ncb, cpc, grid, ncw, threads, ctas;
   int xcols, ocols, dycols;
   uint32_t x_bytes, o_bytes, dy_bytes, stage_bytes;
   size_t smem;
@@ -94,11 +94,20 @@ inline bool v7_plan(const MrlaLightArgs& a, int kind, bool xf, V7Plan* p) {
   const int es = a.dtype == MRLA_F32 ? 4 : 2;
   // W > 56 (mmdet feature maps): column tiles of 8 groups of 7 columns; halo columns of a tile are real data of its
   // neighbours (the TMA box simply starts one / two columns to the left), only image borders are masked
-  const int NQ = a.W > 8 * kV7 ? 8 : (a.W + kV7 - 1) / kV7;
+  int NQ = a.W > 8 * kV7 ? 8 : (a.W + kV7 - 1) / kV7;
+  // small batches of wide maps (detection: 2 images per GPU): one work unit per column tile instead of per image, and
+  // narrower tiles, until the units cover the SMs (identical for all four sweeps: a function of B, C, W only)
+  bool split = false;
+  if (a.W > 8 * kV7 && (int64_t)a.B * (a.C / 64) < kV7SMs) {
+    split = true;
+    if ((int64_t)a.B * ((a.W + 8 * kV7 - 1) / (8 * kV7)) * (a.C / 64) < kV7SMs) NQ = 4;
+  }
   p->NT = (a.W + NQ * kV7 - 1) / (NQ * kV7);
+  p->TPU = split ? 1 : p->NT;
+  p->U = split ? a.B * p->NT : a.B;
   int CB = 0;
   for (int cb : {256, 128, 64})
-    if (a.C % cb == 0 && NQ * cb / 2 <= 256) { CB = cb; break; }
+    if (a.C % cb == 0 && NQ * cb / 2 <= 256 && !(split && cb > 64)) { CB = cb; break; }
   if (CB == 0) return false;
   p->CB = CB; p->NQ = NQ;
   p->ncw = NQ * CB / 64;
@@ -134,7 +143,7 @@ inline bool v7_plan(const MrlaLightArgs& a, int kind, bool xf, V7Plan* p) {
   p->ncb = a.C / CB;
   int cpc = (kV7SMs * p->ctas) / p->ncb;
   if (cpc < 1) cpc = 1;
-  if (cpc > a.B) cpc = a.B;
+  if (cpc > p->U) cpc = p->U;
   p->cpc = cpc;
   p->grid = p->ncb * cpc;
   p->ragged = (a.W % kV7) != 0 || p->NT > 1;
@@ -152,7 +161,7 @@ inline bool v7_virtual_x_ok(const MrlaLightArgs& a) {
 
 inline void v7_fill(V7Params* P, const MrlaLightArgs& a, const V7Plan& p) {
   P->B = a.B; P->C = a.C; P->H = a.H; P->W = a.W;
-  P->NQ = p.NQ; P->NT = p.NT; P->ncb = p.ncb; P->S = p.S; P->cpc = p.cpc; P->rev = 0; P->ncw = p.ncw; P->hint = 0;
+  P->NQ = p.NQ; P->NT = p.NT; P->U = p.U; P->TPU = p.TPU; P->ncb = p.ncb; P->S = p.S; P->cpc = p.cpc; P->rev = 0; P->ncw = p.ncw; P->hint = 0;
   P->x_bytes = p.x_bytes; P->o_bytes = p.o_bytes; P->dy_bytes = p.dy_bytes; P->stage_bytes = p.stage_bytes;
   P->xo_cols = 0;
   P->wv = a.wv; P->zcoef = a.z_coef; P->coef = a.coef; P->mom = nullptr; P->res = a.residual ? 1.f : 0.f;
@@ -182,6 +191,11 @@ int v7_launch_fwd(const MrlaLightArgs& a, cudaStream_t st, const V7Plan& p, bool
   P.mom = mom;
   P.rev = rev;
   P.hint = hint;
+  if (p.TPU != p.NT && MODE != 1 && mom != nullptr) {   // per-tile units add their moments atomically
+    const size_t nacc = MODE == 0 ? 6 : 3;
+    cudaError_t em = cudaMemsetAsync(mom, 0, nacc * (size_t)a.B * a.C * sizeof(float), st);
+    if (em != cudaSuccess) return (int)em;
+  }
   constexpr bool LEAN = std::is_same<T, __nv_bfloat16>::value;   // only bf16 instantiates the non-ragged variant
   const bool ragged = p.ragged || !LEAN;
   cudaError_t e = cudaSuccess;

@@ -122,11 +122,14 @@ def test_bn3_tail_virtual_x_vs_oracle(C, HW, dtype, B, cuda_device):
     torch.cuda.empty_cache()
 
 
-@pytest.mark.parametrize("shape", [(2, 64, 20, 100), (3, 128, 9, 57), (1, 256, 200, 304), (2, 512, 100, 152)])
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 64, 20, 100), (3, 128, 9, 57), (1, 256, 200, 304), (2, 512, 100, 152),
+                                   (40, 256, 12, 70), (160, 64, 6, 113)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])   # fp32 stages of 8 column groups do not fit smem
 def test_bn3_tail_virtual_x_wide_maps_vs_oracle(shape, dtype, cuda_device):
     """W > 56 (the detection backbone's feature maps, mmdetection/.../resnet_mrlal.py: 200x304 at stage 1 for an 800x1216
-    image): the v7 sweeps walk each image in column tiles of 56; tile halos are the neighbouring tile's real columns."""
+    image): the v7 sweeps walk each image in column tiles of 56; tile halos are the neighbouring tile's real columns.
+    Small batches (the first four shapes) spread the tiles of one image over CTAs and add the moments atomically; the last
+    two shapes keep one image per work unit."""
     B, C, H, W = shape
     dev = cuda_device
     c3, idt, dy, P, ds, k = _bn3_tail_case(B, C, (H, W), dtype, dev, seed=C + W, drop=False)

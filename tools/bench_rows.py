@@ -140,7 +140,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--json", default=None)
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--only", default=None, help="base: only the MRLA-base stage rows")
+    ap.add_argument("--only", default=None, help="base: only the MRLA-base stage rows; wide: only the W > 56 rows")
     args = ap.parse_args()
     bf = torch.bfloat16
     out = {}
@@ -148,6 +148,18 @@ def main():
         out["A6_base_stage_resnet50_bf16_nhwc_B256"] = [base_case(256, C, H, 16, T, bf) for C, H, T in
                                                         ((256, 56, 3), (512, 28, 4), (1024, 14, 6), (2048, 7, 3))]
         print(json.dumps(out["A6_base_stage_resnet50_bf16_nhwc_B256"]), flush=True)
+        if args.json:
+            json.dump(out, open(args.json, "w"), indent=1)
+        return
+    if args.only == "wide":
+        # feature maps wider than 56: a detection backbone at 800x1216 with 2 images per GPU (mmdetection's
+        # resnet_mrlal.py) and a 448^2 classification batch
+        out["F4_light_tail_mmdet_800x1216_bf16_nhwc_B2"] = [light_case(2, C, H, W, 32, bf) for C, H, W in
+                                                            ((256, 200, 304), (512, 100, 152), (1024, 50, 76), (2048, 25, 38))]
+        print(json.dumps(out["F4_light_tail_mmdet_800x1216_bf16_nhwc_B2"]), flush=True)
+        out["A4_light_tail_resnet50_448px_bf16_nhwc_B64"] = [light_case(64, C, H, H, 32, bf) for C, H in
+                                                             ((256, 112), (512, 56), (1024, 28), (2048, 14))]
+        print(json.dumps(out["A4_light_tail_resnet50_448px_bf16_nhwc_B64"]), flush=True)
         if args.json:
             json.dump(out, open(args.json, "w"), indent=1)
         return
