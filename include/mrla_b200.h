@@ -330,6 +330,10 @@ int mrla_layernorm_backward(const MrlaLnArgs* a, void* stream);
  * (bench.py reports it as gpu_launches). */
 int mrla_last_launch_count(void);
 
+/* "file:line" inside the library where this thread's last MRLA_ERR_UNSUPPORTED was raised ("" if none): tells a
+ * tensor-map refusal from a planner refusal.  Diagnostic only. */
+const char* mrla_last_error_site(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,7 +92,7 @@ _lib = None
 _lock = threading.Lock()
 
 EXPORTS = (
-    "mrla_abi_version", "mrla_build_info", "mrla_last_launch_count", "mrla_sizeof_light_args",
+    "mrla_abi_version", "mrla_build_info", "mrla_last_launch_count", "mrla_last_error_site", "mrla_sizeof_light_args",
     "mrla_light_bwd_scratch_bytes", "mrla_light_bwd_fuses_relu", "mrla_light_fwd_folds_bn", "mrla_light_virtual_x", "mrla_light_forward", "mrla_light_backward",
     "mrla_nchw_to_nhwc", "mrla_add_relu", "mrla_sizeof_base_args", "mrla_base_bwd_scratch_bytes", "mrla_base_forward", "mrla_base_backward",
     "mrla_maxpool3x3s2_forward", "mrla_maxpool3x3s2_backward",
@@ -122,6 +122,7 @@ def lib() -> ctypes.CDLL:
             raise RuntimeError(f"libmrla_b200.so ABI {L.mrla_abi_version()} != expected {ABI_VERSION}; rebuild")
         L.mrla_build_info.restype = ctypes.c_char_p
         L.mrla_last_launch_count.restype = ctypes.c_int
+        L.mrla_last_error_site.restype = ctypes.c_char_p
         L.mrla_sizeof_light_args.restype = ctypes.c_size_t
         if L.mrla_sizeof_light_args() != ctypes.sizeof(MrlaLightArgs):
             raise RuntimeError("MrlaLightArgs layout mismatch between _lib.py and include/mrla_b200.h")
@@ -190,5 +191,6 @@ def check(rc: int, what: str):
     if rc == 0:
         return
     if rc < 0:
-        raise RuntimeError(f"{what}: {ERRORS.get(rc, rc)}")
+        site = lib().mrla_last_error_site().decode() if rc == -4 else ""
+        raise RuntimeError(f"{what}: {ERRORS.get(rc, rc)}" + (f" [{site.rsplit('/', 1)[-1]}]" if site else ""))
     raise RuntimeError(f"{what}: CUDA error {rc} at launch")

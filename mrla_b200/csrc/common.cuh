@@ -152,4 +152,11 @@ __device__ __forceinline__ void reduce_over_columns(const float (&v)[NV], float*
   __syncthreads();
 }
 
+
+// where the last negative return code of this thread was raised ("file:line"): mrla_last_error_site()
+extern thread_local const char* g_err_site;
+#define MRLA_STR2_(x) #x
+#define MRLA_STR_(x) MRLA_STR2_(x)
+#define MRLA_FAIL(code) (::mrla::g_err_site = __FILE__ ":" MRLA_STR_(__LINE__), (code))
+
 }  // namespace mrla

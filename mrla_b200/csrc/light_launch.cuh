@@ -145,13 +145,13 @@ template <typename T, int ACT, int MODE>
 int launch_tma_sweep(const MrlaLightArgs& a, cudaStream_t st, const TmaPlan& p, const void* xptr, int64_t bs_x,
                      const void* optr, int64_t bs_o, const void* dyptr, int64_t bs_dy, float* mom) {
   CUtensorMap tx, to, tdy;
-  if (make_nhwc_tmap(&tx, xptr, a.dtype, a.B, a.C, a.H, a.W, bs_x, p.CB, p.NQ * kCols + 2, p.G)) return MRLA_ERR_UNSUPPORTED;
+  if (make_nhwc_tmap(&tx, xptr, a.dtype, a.B, a.C, a.H, a.W, bs_x, p.CB, p.NQ * kCols + 2, p.G)) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
   if (MODE == 3) to = tx;
   else if (make_nhwc_tmap(&to, optr, a.dtype, a.B, a.C, a.H, a.W, bs_o, p.CB, p.NQ * kCols + ((MODE == 5 || MODE == 6) ? 2 : 0), p.G))
-    return MRLA_ERR_UNSUPPORTED;
+    return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
   tdy = to;
   if ((MODE == 2 || MODE == 4) && make_nhwc_tmap(&tdy, dyptr, a.dtype, a.B, a.C, a.H, a.W, bs_dy, p.CB, p.NQ * kCols, p.G))
-    return MRLA_ERR_UNSUPPORTED;
+    return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
   TmaSweepParams P;
   P.B = a.B; P.C = a.C; P.H = a.H; P.W = a.W;
   P.G = p.G; P.S = p.S; P.NQ = p.NQ; P.ncb = p.ncb; P.items = p.items; P.cons_threads = p.cons_threads;
@@ -175,7 +175,7 @@ int launch_tma_sweep(const MrlaLightArgs& a, cudaStream_t st, const TmaPlan& p, 
   if (p.CB == 64) MRLA_TMA_LAUNCH(64)
   else if (p.CB == 128) MRLA_TMA_LAUNCH(128)
   else {
-    if (ACT == 1) return MRLA_ERR_UNSUPPORTED;
+    if (ACT == 1) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
     MRLA_TMA_LAUNCH(ACT == 1 ? 128 : 256)
   }
 #undef MRLA_TMA_LAUNCH
@@ -235,9 +235,9 @@ inline bool make_tma_bwd_plan(const MrlaLightArgs& a, TmaBwdPlan* p) {
 template <typename T, int ACT>
 int launch_tma_bwd(const MrlaLightArgs& a, cudaStream_t st, const TmaBwdPlan& p, float* wv_part) {
   CUtensorMap tx, tdy, to;
-  if (make_nhwc_tmap(&tx, a.x, a.dtype, a.B, a.C, a.H, a.W, a.bs_x, p.CB, p.NQ * kCols + 4, p.G)) return MRLA_ERR_UNSUPPORTED;
-  if (make_nhwc_tmap(&tdy, a.dy, a.dtype, a.B, a.C, a.H, a.W, a.bs_dy, p.CB, p.NQ * kCols + 2, p.G)) return MRLA_ERR_UNSUPPORTED;
-  if (make_nhwc_tmap(&to, a.o, a.dtype, a.B, a.C, a.H, a.W, a.bs_o, p.CB, p.NQ * kCols + 2, p.G)) return MRLA_ERR_UNSUPPORTED;
+  if (make_nhwc_tmap(&tx, a.x, a.dtype, a.B, a.C, a.H, a.W, a.bs_x, p.CB, p.NQ * kCols + 4, p.G)) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
+  if (make_nhwc_tmap(&tdy, a.dy, a.dtype, a.B, a.C, a.H, a.W, a.bs_dy, p.CB, p.NQ * kCols + 2, p.G)) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
+  if (make_nhwc_tmap(&to, a.o, a.dtype, a.B, a.C, a.H, a.W, a.bs_o, p.CB, p.NQ * kCols + 2, p.G)) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
   cudaError_t e = cudaMemsetAsync(wv_part, 0, (size_t)p.maxslots * a.C * 9 * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
   TmaBwdParams P;
@@ -262,7 +262,7 @@ int launch_tma_bwd(const MrlaLightArgs& a, cudaStream_t st, const TmaBwdPlan& p,
   if (p.CB == 64) MRLA_TMA_LAUNCH(64)
   else if (p.CB == 128) MRLA_TMA_LAUNCH(128)
   else {
-    if (ACT == 1) return MRLA_ERR_UNSUPPORTED;
+    if (ACT == 1) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
     MRLA_TMA_LAUNCH(ACT == 1 ? 128 : 256)
   }
 #undef MRLA_TMA_LAUNCH
@@ -325,11 +325,11 @@ template <typename T, int ACT>
 int launch_tma_bwd_ring(const MrlaLightArgs& a, cudaStream_t st, const TmaBwdPlan& p, float* wv_part) {
   const int KC = p.big ? 8 : 4;
   CUtensorMap tx, tdy, to, tdx, tdo;
-  if (make_nhwc_tmap(&tx, a.x, a.dtype, a.B, a.C, a.H, a.W, a.bs_x, p.CB, p.NQ * KC + 2, 1)) return MRLA_ERR_UNSUPPORTED;
-  if (make_nhwc_tmap(&tdy, a.dy, a.dtype, a.B, a.C, a.H, a.W, a.bs_dy, p.CB, p.NQ * KC, 1)) return MRLA_ERR_UNSUPPORTED;
-  if (make_nhwc_tmap(&to, a.o, a.dtype, a.B, a.C, a.H, a.W, a.bs_o, p.CB, p.NQ * KC, 1)) return MRLA_ERR_UNSUPPORTED;
-  if (make_nhwc_tmap(&tdx, a.dx, a.dtype, a.B, a.C, a.H, a.W, a.bs_dx, p.CB, p.NQ * KC, 1)) return MRLA_ERR_UNSUPPORTED;
-  if (make_nhwc_tmap(&tdo, a.dout, a.dtype, a.B, a.C, a.H, a.W, a.bs_do, p.CB, p.NQ * KC, 1)) return MRLA_ERR_UNSUPPORTED;
+  if (make_nhwc_tmap(&tx, a.x, a.dtype, a.B, a.C, a.H, a.W, a.bs_x, p.CB, p.NQ * KC + 2, 1)) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
+  if (make_nhwc_tmap(&tdy, a.dy, a.dtype, a.B, a.C, a.H, a.W, a.bs_dy, p.CB, p.NQ * KC, 1)) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
+  if (make_nhwc_tmap(&to, a.o, a.dtype, a.B, a.C, a.H, a.W, a.bs_o, p.CB, p.NQ * KC, 1)) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
+  if (make_nhwc_tmap(&tdx, a.dx, a.dtype, a.B, a.C, a.H, a.W, a.bs_dx, p.CB, p.NQ * KC, 1)) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
+  if (make_nhwc_tmap(&tdo, a.dout, a.dtype, a.B, a.C, a.H, a.W, a.bs_do, p.CB, p.NQ * KC, 1)) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
   cudaError_t e = cudaSuccess;
   TmaBwdParams P;
   P.B = a.B; P.C = a.C; P.H = a.H; P.W = a.W;
@@ -362,7 +362,7 @@ int launch_tma_bwd_ring(const MrlaLightArgs& a, cudaStream_t st, const TmaBwdPla
   if (p.CB == 64) MRLA_TMA_LAUNCH(64)
   else if (p.CB == 128) MRLA_TMA_LAUNCH(128)
   else {
-    if (ACT == 1) return MRLA_ERR_UNSUPPORTED;
+    if (ACT == 1) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
     MRLA_TMA_LAUNCH(ACT == 1 ? 128 : 256)
   }
 #undef MRLA_TMA_LAUNCH
@@ -414,7 +414,7 @@ int light_forward_impl(const MrlaLightArgs& a, cudaStream_t st) {
   if (a.x_virtual) {
     if (!(v7_base && full && a.z && a.z_coef && v7_ptr_ok(a.z, a.bs_z, es) && v7_plan(a, V7_S1, true, &v1) &&
           v7_plan(a, V7_S2, true, &v2)))
-      return MRLA_ERR_UNSUPPORTED;   // callers ask mrla_light_virtual_x() first
+      return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);   // callers ask mrla_light_virtual_x() first
   }
   const bool v7x = a.x_virtual != 0;
   const bool v7p = !v7x && v7_base && a.z == nullptr && v7_ptr_ok(a.x, a.bs_x, es) && v7_plan(a, V7_S1, false, &v1) &&
@@ -438,7 +438,7 @@ int light_forward_impl(const MrlaLightArgs& a, cudaStream_t st) {
     if (rc) return rc;
     x_ready = true;
   } else {
-    if (a.z_coef) return MRLA_ERR_UNSUPPORTED;   // callers ask mrla_light_fwd_folds_bn() first
+    if (a.z_coef) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);   // callers ask mrla_light_fwd_folds_bn() first
     if (!x_ready) {
       const int64_t n = (int64_t)a.C * a.H * a.W;
       const int64_t v = 16 / es;
@@ -532,13 +532,13 @@ int light_backward_impl(const MrlaLightArgs& a, cudaStream_t st) {
   if (v7x) {
     if (!(v7_base && a.fuse_relu_bwd && a.bn_mode == MRLA_BN_TRAIN && a.z && a.z_coef && v7_ptr_ok(a.z, a.bs_z, es_) &&
           v7_plan(a, V7_SA, true, &va) && v7_plan(a, V7_SB, true, &vb)))
-      return MRLA_ERR_UNSUPPORTED;   // callers ask mrla_light_virtual_x() first
+      return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);   // callers ask mrla_light_virtual_x() first
   }
   const bool v7p = !v7x && v7_base && !a.fuse_relu_bwd && v7_ptr_ok(a.x, a.bs_x, es_) && v7_plan(a, V7_SA, false, &va) &&
                    v7_plan(a, V7_SB, false, &vb);
   const bool v7 = v7x || v7p;
   const bool tma_r = !v7 && tma_b && tma_ptr_ok(a.dx, a.bs_dx, es_) && tma_ptr_ok(a.dout, a.bs_do, es_) && make_tma_ring_plan(a, &tpr);
-  if (a.fuse_relu_bwd && !tma_r && !v7x) return MRLA_ERR_UNSUPPORTED;   // callers ask mrla_light_bwd_fuses_relu() first
+  if (a.fuse_relu_bwd && !tma_r && !v7x) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);   // callers ask mrla_light_bwd_fuses_relu() first
   const int nparts = v7 ? vb.cpc : (tma_r ? tpr.maxslots : (tma_b ? tpb.maxslots : pb.grid_y));
   const size_t nfl = (size_t)nparts * a.C * 9 + (size_t)a.B * 2 * a.k_size + (v7x ? (size_t)vb.cpc * 2 * a.C : 0);
   const size_t need = nfl * sizeof(float);
@@ -635,7 +635,7 @@ int light_dispatch(const MrlaLightArgs& a, cudaStream_t st) {
   return BWD ? light_backward_impl<T, LAYOUT, CV, CVB, ACT, HAS_O>(a, st)             \
              : light_forward_impl<T, LAYOUT, CV, ACT, HAS_O>(a, st)
   if (a.layout == MRLA_NCHW) {
-    if (a.act != MRLA_ACT_NONE) return MRLA_ERR_UNSUPPORTED;  // GELU variant is token-layout only (DeiT)
+    if (a.act != MRLA_ACT_NONE) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);  // GELU variant is token-layout only (DeiT)
     if (has_o) { MRLA_GO(0, 1, 1, 0, true); } else { MRLA_GO(0, 1, 1, 0, false); }
   } else {
     if (a.C % 4) return MRLA_ERR_ALIGN;

@@ -1,5 +1,6 @@
 // Host side of the v7 sweeps (light_v7.cuh): planning, cached tensor maps, launches.
 #pragma once
+#include <cstdio>
 #include <mutex>
 #include <type_traits>
 #include <unordered_map>
@@ -10,6 +11,7 @@
 namespace mrla {
 
 extern thread_local int g_launch_count;
+extern thread_local char g_err_detail[192];
 constexpr int kV7SMs = 148;
 
 // ------------------------------------------------------------------------------------ tensor-map cache
@@ -44,6 +46,10 @@ inline int cached_nhwc_tmap(CUtensorMap* out, const void* base, int dtype, int B
     return 0;
   }
   const int rc = make_nhwc_tmap(out, base, dtype, B, C, H, W, bs, box_c, box_w, box_h);
+  if (rc != 0) {
+    snprintf(g_err_detail, sizeof(g_err_detail), "tensor map rc=%d base=%p dtype=%d B=%d C=%d H=%d W=%d bs=%lld box=(%d,%d,%d)", rc,
+             base, dtype, B, C, H, W, (long long)bs, box_c, box_w, box_h);
+  }
   if (rc == 0) {
     if (cache.size() > 8192) cache.clear();
     cache.emplace(key, *out);
@@ -180,12 +186,12 @@ template <typename T, int MODE>
 int v7_launch_fwd(const MrlaLightArgs& a, cudaStream_t st, const V7Plan& p, bool xf, const void* xsrc, int64_t bs_x,
                   float* mom, int rev, int hint) {
   CUtensorMap tx, to, tdy, ty;
-  if (cached_nhwc_tmap(&tx, xsrc, a.dtype, a.B, a.C, a.H, a.W, bs_x, p.CB, p.xcols, 1)) return MRLA_ERR_UNSUPPORTED;
-  if (cached_nhwc_tmap(&to, a.o, a.dtype, a.B, a.C, a.H, a.W, a.bs_o, p.CB, p.ocols, 1)) return MRLA_ERR_UNSUPPORTED;
+  if (cached_nhwc_tmap(&tx, xsrc, a.dtype, a.B, a.C, a.H, a.W, bs_x, p.CB, p.xcols, 1)) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
+  if (cached_nhwc_tmap(&to, a.o, a.dtype, a.B, a.C, a.H, a.W, a.bs_o, p.CB, p.ocols, 1)) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
   tdy = to;
   ty = to;
-  if (MODE == 2 && cached_nhwc_tmap(&tdy, a.dy, a.dtype, a.B, a.C, a.H, a.W, a.bs_dy, p.CB, p.dycols, 1)) return MRLA_ERR_UNSUPPORTED;
-  if (MODE == 1 && cached_nhwc_tmap(&ty, a.y, a.dtype, a.B, a.C, a.H, a.W, a.bs_y, 64, kV7, 1)) return MRLA_ERR_UNSUPPORTED;
+  if (MODE == 2 && cached_nhwc_tmap(&tdy, a.dy, a.dtype, a.B, a.C, a.H, a.W, a.bs_dy, p.CB, p.dycols, 1)) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
+  if (MODE == 1 && cached_nhwc_tmap(&ty, a.y, a.dtype, a.B, a.C, a.H, a.W, a.bs_y, 64, kV7, 1)) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
   V7Params P;
   v7_fill(&P, a, p);
   P.mom = mom;
@@ -229,13 +235,13 @@ int v7_launch_fwd(const MrlaLightArgs& a, cudaStream_t st, const V7Plan& p, bool
 template <typename T>
 int v7_launch_bwd(const MrlaLightArgs& a, cudaStream_t st, const V7Plan& p, bool xf, bool fuse, const void* xsrc,
                   int64_t bs_x, float* wv_part, float* dz_part, float* dz_sums) {
-  if (xf != fuse) return MRLA_ERR_UNSUPPORTED;
+  if (xf != fuse) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
   CUtensorMap tx, to, tdy, tdx, tdo;
-  if (cached_nhwc_tmap(&tx, xsrc, a.dtype, a.B, a.C, a.H, a.W, bs_x, p.CB, p.xcols, 1)) return MRLA_ERR_UNSUPPORTED;
-  if (cached_nhwc_tmap(&to, a.o, a.dtype, a.B, a.C, a.H, a.W, a.bs_o, p.CB, p.ocols, 1)) return MRLA_ERR_UNSUPPORTED;
-  if (cached_nhwc_tmap(&tdy, a.dy, a.dtype, a.B, a.C, a.H, a.W, a.bs_dy, p.CB, p.dycols, 1)) return MRLA_ERR_UNSUPPORTED;
-  if (cached_nhwc_tmap(&tdx, a.dx, a.dtype, a.B, a.C, a.H, a.W, a.bs_dx, 64, kV7, 1)) return MRLA_ERR_UNSUPPORTED;
-  if (cached_nhwc_tmap(&tdo, a.dout, a.dtype, a.B, a.C, a.H, a.W, a.bs_do, 64, kV7, 1)) return MRLA_ERR_UNSUPPORTED;
+  if (cached_nhwc_tmap(&tx, xsrc, a.dtype, a.B, a.C, a.H, a.W, bs_x, p.CB, p.xcols, 1)) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
+  if (cached_nhwc_tmap(&to, a.o, a.dtype, a.B, a.C, a.H, a.W, a.bs_o, p.CB, p.ocols, 1)) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
+  if (cached_nhwc_tmap(&tdy, a.dy, a.dtype, a.B, a.C, a.H, a.W, a.bs_dy, p.CB, p.dycols, 1)) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
+  if (cached_nhwc_tmap(&tdx, a.dx, a.dtype, a.B, a.C, a.H, a.W, a.bs_dx, 64, kV7, 1)) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
+  if (cached_nhwc_tmap(&tdo, a.dout, a.dtype, a.B, a.C, a.H, a.W, a.bs_do, 64, kV7, 1)) return MRLA_FAIL(MRLA_ERR_UNSUPPORTED);
   V7Params P;
   v7_fill(&P, a, p);
   P.rev = 1;    // sweep A walked the batch upwards

@@ -4,6 +4,9 @@
 
 namespace mrla {
 thread_local int g_launch_count = 0;
+thread_local const char* g_err_site = "";
+thread_local char g_err_detail[192] = "";
+static thread_local char g_err_msg[512];
 extern template int light_forward_t<float>(const MrlaLightArgs&, cudaStream_t);
 extern template int light_backward_t<float>(const MrlaLightArgs&, cudaStream_t);
 extern template int light_forward_t<__nv_bfloat16>(const MrlaLightArgs&, cudaStream_t);
@@ -87,6 +90,10 @@ const char* mrla_build_info(void) {
 }
 
 int mrla_last_launch_count(void) { return g_launch_count; }
+const char* mrla_last_error_site(void) {
+  snprintf(g_err_msg, sizeof(g_err_msg), "%s%s%s", g_err_site, g_err_detail[0] ? " " : "", g_err_detail);
+  return g_err_msg;
+}
 
 size_t mrla_sizeof_light_args(void) { return sizeof(MrlaLightArgs); }
 
@@ -113,6 +120,8 @@ int mrla_light_virtual_x(const MrlaLightArgs* a) {
 int mrla_light_forward(const MrlaLightArgs* a, void* stream) {
   NvtxRange nvtx_("mrla_light_forward");
   g_launch_count = 0;
+  g_err_site = "";
+  g_err_detail[0] = 0;
   int rc = check_common(a, false);
   if (rc) return rc;
   if (!a->y || !a->coef) return MRLA_ERR_NULL;
@@ -127,6 +136,8 @@ int mrla_light_forward(const MrlaLightArgs* a, void* stream) {
 int mrla_light_backward(const MrlaLightArgs* a, void* stream) {
   NvtxRange nvtx_("mrla_light_backward");
   g_launch_count = 0;
+  g_err_site = "";
+  g_err_detail[0] = 0;
   int rc = check_common(a, true);
   if (rc) return rc;
   if (!a->dy || !a->dx || !a->gmom || !a->bcoef || !a->scratch) return MRLA_ERR_NULL;

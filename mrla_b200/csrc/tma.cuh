@@ -118,6 +118,13 @@ inline int make_nhwc_tmap(CUtensorMap* out, const void* base, int dtype, int B, 
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(out, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_ERROR_INVALID_CONTEXT) {
+    // a thread that has not made a runtime call yet (autograd's backward thread on its first node) has no current
+    // context, which the driver-API encode wants: bind the runtime's primary context and retry
+    cudaFree(nullptr);
+    r = enc(out, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
 }
 
