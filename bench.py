@@ -273,7 +273,9 @@ def run_product_arm(args):
     else:
         from mrla_b200.resnet_mrla_light import resnet50_mrlal as factory
         metric, model_name = METRIC, "resnet50_mrlal"
-    model = factory(drop_path=args.drop_path).to(dev).to(memory_format=torch.channels_last).train()
+    model = factory(drop_path=args.drop_path).to(dev).train()
+    if not args.nchw:   # --nchw: the stock reference call path (train.py never asks for channels_last)
+        model = model.to(memory_format=torch.channels_last)
     opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)  # reference train.py:199
     net = model
     if world > 1 and args.no_graph:   # eager path: the reference's DDP wrap; the graph path all-reduces a flat buffer
@@ -291,8 +293,11 @@ def run_product_arm(args):
     def normalise(u8_nhwc):   # [B,224,224,3] uint8 on device -> [B,3,224,224] bf16, channels_last strides (no transpose)
         return u8_nhwc.permute(0, 3, 1, 2).float().sub_(mean).mul_(inv_std).to(torch.bfloat16)
 
+    if args.nchw:
+        normalise_cl = normalise
+        normalise = lambda u8: normalise_cl(u8).contiguous()   # dense NCHW, as torchvision's ToTensor pipeline delivers
     dev_img = normalise(host_img[0].to(dev))
-    assert dev_img.is_contiguous(memory_format=torch.channels_last)
+    assert args.nchw or dev_img.is_contiguous(memory_format=torch.channels_last)
     dev_lbl = host_lbl[0].to(dev)
 
     def step(img, lbl):
@@ -492,7 +497,7 @@ def run_product_arm(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{model_name} training step (fwd+loss+bwd+SGD), BASELINE configs[{2 if args.config == 'mrlab' else 1}]",
                    "model": model_name, "per_gpu_batch": B, "global_batch": B * world, "image": "3x224x224",
-                   "precision": "bf16 autocast, fp32 master weights", "memory_format": "channels_last",
+                   "precision": "bf16 autocast, fp32 master weights", "memory_format": "nchw model + images (promoted by the product model)" if args.nchw else "channels_last",
                    "drop_path": args.drop_path,
                    "host_batch": "e2e: pinned uint8 HWC images + int64 labels copied H2D every step, normalised to bf16 "
                                  "channels_last on the device",
@@ -660,6 +665,9 @@ def main():
                     help="N > 1: bucketed gradient all-reduce overlapped with backward instead of one all-reduce after it")
     ap.add_argument("--capture-comm", action="store_true",
                     help="N > 1: capture the flat-gradient all-reduce inside graph A instead of issuing it between the graphs")
+    ap.add_argument("--nchw", action="store_true",
+                    help="leave model and images in the stock NCHW layout of the reference's train.py (the product model "
+                         "promotes the image batch to channels_last itself)")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the same-GPU eager PyTorch baseline")
     ap.add_argument("--compile-baseline", action="store_true", help="also time the eager baseline under torch.compile")
     args = ap.parse_args()

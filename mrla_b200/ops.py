@@ -196,7 +196,20 @@ class _ToNHWC(torch.autograd.Function):
 
 def _want_nhwc(x: torch.Tensor) -> bool:
     B, C, H, W = x.shape
-    return PROMOTE_NCHW and x.numel() >= PROMOTE_MIN_ELEMS and C % 8 == 0 and W <= 56 and H * W > 1
+    # W > 56 runs the column-tiled v7 sweeps, which exist for 16-bit storage only
+    wmax = 512 if x.dtype in (torch.bfloat16, torch.float16) else 56
+    return PROMOTE_NCHW and x.numel() >= PROMOTE_MIN_ELEMS and C % 8 == 0 and W <= wmax and H * W > 1
+
+
+def promote_images(x: torch.Tensor) -> torch.Tensor:
+    """The image batch at the network input, made channels_last (one copy of a 3-channel tensor) when it arrives as a
+    dense NCHW CUDA tensor: the reference's train.py never asks for channels_last (resnet/train.py:387), and with this the
+    stem conv already produces NHWC, so every BatchNorm / pooling / tail kernel of the model runs its fast layout
+    without touching train.py.  Values are unchanged; only strides differ."""
+    if (PROMOTE_NCHW and x.is_cuda and x.dim() == 4 and x.shape[1] > 1
+            and not x.is_contiguous(memory_format=torch.channels_last)):
+        return x.contiguous(memory_format=torch.channels_last)
+    return x
 
 
 # --------------------------------------------------------------------------------- the fused op

@@ -11,7 +11,7 @@ import torch.nn.functional as F
 from . import _lib
 from .drop import DropPath
 from .modules.mrla_base_module import mrla_base_layer
-from .ops import bn_act, is_plain_batchnorm, max_pool
+from .ops import bn_act, is_plain_batchnorm, max_pool, promote_images
 from .resnet_mrla_light import _bn_effective_momentum, _conv1x1, _conv3x3
 
 __all__ = ["ResNet_mrlab", "MRLA_Bottleneck", "mrla_module", "mrla_base_block_tail", "resnet50_mrlab",
@@ -153,7 +153,7 @@ class ResNet_mrlab(nn.Module):
         return nn.ModuleList(seq)
 
     def forward_features(self, x):
-        x = max_pool(bn_act(self.conv1(x), self.bn1, relu=True), self.maxpool)
+        x = max_pool(bn_act(self.conv1(promote_images(x)), self.bn1, relu=True), self.maxpool)
         k = v = None
         for stage in self.stages:
             for blk in stage:

@@ -17,7 +17,7 @@ from . import _lib
 from .drop import DropPath
 from .modules.mrla_light_module import mrla_light_layer
 from .ops import (bn3_light_tail, bn3_tail_eligible, bn_act, effective_momentum, is_plain_batchnorm, light_tail,
-                  max_pool)
+                  max_pool, promote_images)
 
 __all__ = ["ResNet_mrlal", "MRLA_Bottleneck", "mrla_module", "mrla_light_block_tail",
            "resnet50_mrlal", "resnet101_mrlal"]
@@ -191,7 +191,7 @@ class ResNet_mrlal(nn.Module):
         return nn.Sequential(*seq)
 
     def forward_features(self, x):
-        x = max_pool(bn_act(self.conv1(x), self.bn1, relu=True), self.maxpool)
+        x = max_pool(bn_act(self.conv1(promote_images(x)), self.bn1, relu=True), self.maxpool)
         return self.layer4(self.layer3(self.layer2(self.layer1(x))))
 
     def forward(self, x):

@@ -138,3 +138,13 @@ def test_light_args_mirror_has_the_producer_fold_fields():
     assert _lib.ABI_VERSION == 4
     bn = [f[0] for f in _lib.MrlaBnArgs._fields_]
     assert bn[6] == "stats_only" and bn[-1] == "sums"
+
+
+def test_promote_images_is_identity_off_gpu():
+    """ops.promote_images only re-strides dense NCHW CUDA batches; CPU tensors (and the oracle's inputs) pass through."""
+    import torch
+    from mrla_b200.ops import promote_images
+    x = torch.randn(2, 3, 8, 8)
+    assert promote_images(x) is x
+    y = torch.randn(2, 8)
+    assert promote_images(y) is y
