@@ -32,6 +32,7 @@ struct V7Params {
   int B, C, H, W;
   int NQ, ncb, S, cpc;     // column groups, channel blocks, pipeline stages, CTAs per channel block (grid = ncb*cpc)
   int NT;                  // column tiles of NQ*7 columns per image (W > 56: mmdet feature maps); 1 otherwise
+  uint32_t mH, mPU, mNS;   // ceil(2^32 / d) for d = H, TPU*H, NT/TPU (v7_fdiv; exact for a*d < 2^32)
   int U, TPU;              // work units and column tiles per unit: (B, NT) = one unit per image, or (B*NT, 1) = one unit per
                            // tile for small batches (the per-image moments are then accumulated with atomics)
   int rev;                 // 1: walk the batch from the last sample down (the previous sweep left that end in L2)
@@ -52,6 +53,8 @@ struct V7Params {
 };
 
 // ---------------------------------------------------------------------------- small helpers
+// a / d for 0 <= a, a*d < 2^32, with m = ceil(2^32 / d) from the host (d == 1: m is unused)
+__device__ __forceinline__ int v7_fdiv(int a, int d, uint32_t m) { return d == 1 ? a : (int)__umulhi((uint32_t)a, m); }
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -125,7 +128,7 @@ __device__ __forceinline__ void v7_producer(const CUtensorMap* tm0, const CUtens
   uint32_t ph = 1;   // first pass over the ring: slots are free
   const int NS = P.NT / P.TPU;   // units per image
   for (int u = m; u < P.U; u += P.cpc) {
-    const int bi = u / NS, tile0 = (u - bi * NS) * P.TPU;
+    const int bi = v7_fdiv(u, NS, P.mNS), tile0 = (u - bi * NS) * P.TPU;
     const int b = P.rev ? P.B - 1 - bi : bi;
     for (int tile = tile0; tile < tile0 + P.TPU; ++tile) {
       const int t0 = tile * P.NQ * kV7;   // first image column of the tile
@@ -387,7 +390,7 @@ k_v7_fwd(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUten
   int red_sel = 0;
   const int NS = P.NT / P.TPU;   // units per image
   for (int u = m; u < P.U; u += P.cpc) {
-    const int bi = u / NS, tile0 = (u - bi * NS) * P.TPU;
+    const int bi = v7_fdiv(u, NS, P.mNS), tile0 = (u - bi * NS) * P.TPU;
     const int b = P.rev ? P.B - 1 - bi : bi;
     S.b = b;
     if (MODE == 1) {
@@ -398,13 +401,9 @@ k_v7_fwd(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUten
     }
 #pragma unroll
     for (int i = 0; i < (F::NACC > 0 ? F::NACC : 1); ++i) { S.acc[i] = f2(0.f, 0.f); S.accb[i] = f2(0.f, 0.f); }
-    if (P.NT == 1) {
-      S.image();
-    } else {
-      for (int tile = tile0; tile < tile0 + P.TPU; ++tile) {   // W > 56: column tiles; the moments run over all of them
-        S.set_tile(tile * P.NQ * K, q);
-        S.image();
-      }
+    for (int tile = tile0; tile < tile0 + P.TPU; ++tile) {   // W > 56: column tiles; the moments run over all of them
+      if (P.NT > 1) S.set_tile(tile * P.NQ * K, q);
+      S.image();                                              // (one call site: the body is ~10k instructions)
     }
     if (F::NACC > 0) {
       if (P.NQ == 1) {
@@ -497,10 +496,10 @@ struct V7Bwd {
   // request global row g (of this CTA's row sequence) into stage sx
   __device__ __forceinline__ void issue_row(int g, int sx) {
     const int per_unit = P.TPU * P.H, NS = P.NT / P.TPU;
-    const int ui = g / per_unit, rem = g - ui * per_unit;
-    const int t = rem / P.H, row = rem - t * P.H;
+    const int ui = v7_fdiv(g, per_unit, P.mPU), rem = g - ui * per_unit;
+    const int t = v7_fdiv(rem, P.H, P.mH), row = rem - t * P.H;
     const int u = m + ui * P.cpc;
-    const int bi = u / NS;
+    const int bi = v7_fdiv(u, NS, P.mNS);
     const int t0 = ((u - bi * NS) * P.TPU + t) * P.NQ * K;
     const int bb = P.rev ? P.B - 1 - bi : bi;
     const uint32_t fb = bar_s + sx * 8;
@@ -532,7 +531,12 @@ struct V7Bwd {
     if (lane == 0) {
       uint32_t old;
       asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(cnt_s + sx * 4) : "memory");
-      if (((old + 1) % (uint32_t)P.ncw) == 0 && g + P.S < rows_total) issue_row(g + P.S, sx);
+      if (old + 1 == (uint32_t)P.ncw) {
+        // last warp of the round: rearm the counter (nobody touches it before the refilled stage's barrier completes, and
+        // the expect_tx arrive below releases this store), then refill the stage with global row g + S
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(cnt_s + sx * 4), "r"(0u) : "memory");
+        if (g + P.S < rows_total) issue_row(g + P.S, sx);
+      }
     }
   }
 
@@ -804,7 +808,7 @@ k_v7_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUten
   const int64_t BC = (int64_t)P.B * P.C;
   const int NS = P.NT / P.TPU;   // units per image
   for (int u = m; u < P.U; u += P.cpc) {
-    const int bi = u / NS, tile0 = (u - bi * NS) * P.TPU;
+    const int bi = v7_fdiv(u, NS, P.mNS), tile0 = (u - bi * NS) * P.TPU;
     const int b = P.rev ? P.B - 1 - bi : bi;
     S.b = b;
     const float* cp = P.bcoef + (int64_t)b * P.C + c;
@@ -814,13 +818,9 @@ k_v7_bwd(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUten
     S.q3 = *reinterpret_cast<const float2*>(cp + 3 * BC);
     S.ta = *reinterpret_cast<const float2*>(cp + 4 * BC);
     S.dyc = *reinterpret_cast<const float2*>(cp + 5 * BC);
-    if (P.NT == 1) {
+    for (int tile = tile0; tile < tile0 + P.TPU; ++tile) {
+      if (P.NT > 1) S.set_tile(tile * P.NQ * K, q);
       S.image();
-    } else {
-      for (int tile = tile0; tile < tile0 + P.TPU; ++tile) {
-        S.set_tile(tile * P.NQ * K, q);
-        S.image();
-      }
     }
   }
   if (S.lane == 0) bulk_wait_all<0>();

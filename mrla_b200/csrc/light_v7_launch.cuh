@@ -152,6 +152,10 @@ inline bool v7_plan(const MrlaLightArgs& a, int kind, bool xf, V7Plan* p) {
   if (cpc > p->U) cpc = p->U;
   p->cpc = cpc;
   p->grid = p->ncb * cpc;
+  {  // sweep B finds (unit, tile, row) of a pipeline row with multiply-high reciprocals: exact while rows * d < 2^32
+    const uint64_t per_unit = (uint64_t)p->TPU * a.H, n_my = ((uint64_t)p->U + cpc - 1) / cpc;
+    if (n_my * per_unit * per_unit >= ((uint64_t)1 << 32)) return false;
+  }
   p->ragged = (a.W % kV7) != 0 || p->NT > 1;
   return true;
 }
@@ -167,6 +171,9 @@ inline bool v7_virtual_x_ok(const MrlaLightArgs& a) {
 
 inline void v7_fill(V7Params* P, const MrlaLightArgs& a, const V7Plan& p) {
   P->B = a.B; P->C = a.C; P->H = a.H; P->W = a.W;
+  auto magic = [](int d) { return (uint32_t)((((uint64_t)1 << 32) + (uint64_t)d - 1) / (uint64_t)d); };   // d >= 2
+  const int ns = p.NT / p.TPU;
+  P->mH = magic(a.H); P->mPU = magic(p.TPU * a.H); P->mNS = ns > 1 ? magic(ns) : 0;
   P->NQ = p.NQ; P->NT = p.NT; P->U = p.U; P->TPU = p.TPU; P->ncb = p.ncb; P->S = p.S; P->cpc = p.cpc; P->rev = 0; P->ncw = p.ncw; P->hint = 0;
   P->x_bytes = p.x_bytes; P->o_bytes = p.o_bytes; P->dy_bytes = p.dy_bytes; P->stage_bytes = p.stage_bytes;
   P->xo_cols = 0;
