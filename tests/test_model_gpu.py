@@ -14,7 +14,7 @@ def _unzero_bn3(model):
             torch.nn.init.normal_(p, 1.0, 0.2)
 
 
-def _compare(prod, orc, x, tol, l2=False):
+def _compare(prod, orc, x, tol, l2=False, oracle_x=None):
     """`l2`: compare parameter gradients in the L2 norm.  A whole network in fp32 is a chaotic map for single gradient
     elements: product and oracle differ in the last bits of every BatchNorm statistic, which flips a handful of ReLU
     decisions (MRLA-base adds one more ReLU behind bn_mrla) and moves individual elements by percents while every op on its
@@ -22,7 +22,7 @@ def _compare(prod, orc, x, tol, l2=False):
     scattering between 8e-4 and 4e-2 over seeds for round-1 and round-2 builds alike."""
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    yp, yo = prod(x), orc(x)
+    yp, yo = prod(x), orc(x if oracle_x is None else oracle_x)
     assert rel_err(yp, yo) < tol
     yp.square().sum().backward()
     yo.square().sum().backward()
@@ -58,10 +58,13 @@ def test_resnet_mrlal_matches_oracle_model(channels_last, cuda_device):
     x = torch.randn(4, 3, 96, 96, device=dev)
     if channels_last:
         prod = prod.to(memory_format=torch.channels_last)
-        x = x.contiguous(memory_format=torch.channels_last)
-    # gradients in the L2 norm (see _compare): the max-norm figure of single elements scatters around the 4e-3 bound with
-    # the layout the convolutions run in (3.7e-3 channels_last, 4.4e-3 NCHW weights after the stem promotion)
-    _compare(prod, orc, x, 2e-4, l2=True)
+    # The product computes in channels_last either way (ops.promote_images re-strides a dense NCHW batch at the stem), so
+    # the oracle is given the same values in channels_last strides: cuDNN picks other algorithms per layout, and the ORACLE
+    # run in NCHW differs from ITSELF run in channels_last by 6e-3 (L2) / 2.9e-2 (max) in single parameter gradients of
+    # this network (ReLU decisions flip on last-bit differences; profiles/r02_whole_model_noise_floor.txt,
+    # tools/dbg_mrlal.py), while product and oracle in the same layout agree to 9e-5.
+    x = x.contiguous(memory_format=torch.channels_last)
+    _compare(prod, orc, x if channels_last else x.clone(memory_format=torch.contiguous_format), 2e-4, oracle_x=x)
 
 
 def test_resnet_mrlab_matches_oracle_model(cuda_device):
