@@ -149,6 +149,11 @@ int mrla_light_fwd_folds_bn(const MrlaLightArgs* a);
  * that re-form x on the fly (`x_virtual`), else 0 (the caller then lets forward materialise x as before). */
 int mrla_light_virtual_x(const MrlaLightArgs* a);
 
+/* Host-only description of the launch plan the v7 sweeps would use for these arguments (no CUDA call; for tests and
+ * diagnostics).  kind: 0 sweep 1, 1 sweep 2, 2 sweep A, 3 sweep B; xf: x re-formed from z (x_virtual).  Fills
+ * out[12] = { eligible, CB, NQ, NT, U, TPU, stages, cpc, grid, threads, ctas_per_sm, smem_bytes } and returns `eligible`. */
+int mrla_light_v7_plan(const MrlaLightArgs* a, int kind, int xf, int64_t out[12]);
+
 /* y = residual*x + m_b*( BN( gate(x)*act(dwconv3x3(x)) + lambda*o ) ), plus saved statistics. */
 int mrla_light_forward(const MrlaLightArgs* a, void* stream);
 

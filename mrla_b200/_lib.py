@@ -93,7 +93,7 @@ _lock = threading.Lock()
 
 EXPORTS = (
     "mrla_abi_version", "mrla_build_info", "mrla_last_launch_count", "mrla_last_error_site", "mrla_sizeof_light_args",
-    "mrla_light_bwd_scratch_bytes", "mrla_light_bwd_fuses_relu", "mrla_light_fwd_folds_bn", "mrla_light_virtual_x", "mrla_light_forward", "mrla_light_backward",
+    "mrla_light_bwd_scratch_bytes", "mrla_light_bwd_fuses_relu", "mrla_light_fwd_folds_bn", "mrla_light_virtual_x", "mrla_light_v7_plan", "mrla_light_forward", "mrla_light_backward",
     "mrla_nchw_to_nhwc", "mrla_add_relu", "mrla_sizeof_base_args", "mrla_base_bwd_scratch_bytes", "mrla_base_forward", "mrla_base_backward",
     "mrla_maxpool3x3s2_forward", "mrla_maxpool3x3s2_backward",
     "mrla_sizeof_bn_args", "mrla_bn_scratch_bytes", "mrla_bn_forward", "mrla_bn_backward",

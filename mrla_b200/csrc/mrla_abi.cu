@@ -117,6 +117,15 @@ int mrla_light_virtual_x(const MrlaLightArgs* a) {
   return v7_virtual_x_ok(*a) ? 1 : 0;
 }
 
+int mrla_light_v7_plan(const MrlaLightArgs* a, int kind, int xf, int64_t out[12]) {
+  if (a == nullptr || out == nullptr || kind < 0 || kind > 3) return 0;
+  V7Plan p{};
+  const bool ok = v7_plan(*a, kind, xf != 0, &p);
+  const int64_t v[12] = {ok ? 1 : 0, p.CB, p.NQ, p.NT, p.U, p.TPU, p.S, p.cpc, p.grid, p.threads, p.ctas, (int64_t)p.smem};
+  for (int i = 0; i < 12; ++i) out[i] = ok ? v[i] : (i == 0 ? 0 : -1);
+  return ok ? 1 : 0;
+}
+
 int mrla_light_forward(const MrlaLightArgs* a, void* stream) {
   NvtxRange nvtx_("mrla_light_forward");
   g_launch_count = 0;
