@@ -227,6 +227,10 @@ CASES = {
     "light_tail_c2048_k7": (light_tail_case, dict(seed=7, B=2, C=2048, H=2, W=2, d=32, drop_path=0.0, training=True)),
     "light_tail_c96_d8_1x1": (light_tail_case, dict(seed=8, B=5, C=96, H=1, W=1, d=8, drop_path=0.0, training=True)),
     "light_tail_c64_d16_wide": (light_tail_case, dict(seed=9, B=2, C=64, H=2, W=37, d=16, drop_path=0.0, training=True, relu_x=False)),
+    # feature maps wider than 56 columns (detection backbones, mmdetection/mmdet/models/backbones/resnet_mrlal.py:116): the v7
+    # sweeps walk them in column tiles (round 2); train-mode BN and the mmdet setting (eval-mode BN, no DropPath)
+    "light_tail_c64_w75": (light_tail_case, dict(seed=18, B=2, C=64, H=5, W=75, d=32, drop_path=0.0, training=True)),
+    "light_tail_c128_w60_eval": (light_tail_case, dict(seed=19, B=2, C=128, H=4, W=60, d=32, drop_path=0.0, training=False)),
     "base_stage_c64_t3": (base_stage_case, dict(seed=10, B=3, C=64, H=5, W=5, d=16, T=3, drop_path=0.0)),
     "base_stage_c128_t4_drop": (base_stage_case, dict(seed=11, B=4, C=128, H=3, W=4, d=16, T=4, drop_path=0.3)),
     "base_stage_c64_eval": (base_stage_case, dict(seed=12, B=2, C=64, H=5, W=5, d=16, T=2, drop_path=0.2, training=False)),
