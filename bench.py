@@ -533,8 +533,11 @@ def run_product_arm(args):
     if collective_ms is not None:
         line["collective_ms"] = round(collective_ms, 4)
         line["collective"] = {"buckets": len(gstep.buckets), "bytes": int(gstep.flat.numel() * 4),
-                              "what": "device time of the bucketed gradient all-reduce (AVG, fp32) run alone; inside the "
-                                      "step it overlaps backward"}
+                              "what": "device time of the gradient all-reduce (AVG, fp32 flat buffer) run alone; in the step it "
+                                      + ("is launched per bucket from backward hooks on a side stream (--overlap-comm)"
+                                         if args.overlap_comm else
+                                         ("is captured at the end of graph A (--capture-comm)" if args.capture_comm
+                                          else "runs between graph A (fwd+bwd) and graph B (SGD)"))}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
