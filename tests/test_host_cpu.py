@@ -148,3 +148,42 @@ def test_promote_images_is_identity_off_gpu():
     assert promote_images(x) is x
     y = torch.randn(2, 8)
     assert promote_images(y) is y
+
+
+def test_norm_layer_gate_and_momentum_rule():
+    """Only an exact nn.BatchNorm2d takes the fused BatchNorm / tail paths (SyncBatchNorm, GroupNorm and subclasses keep their
+    own module semantics: ADVICE round 1); momentum=None is the cumulative moving average of nn.BatchNorm2d."""
+    import torch
+    import torch.nn as nn
+    from mrla_b200.ops import effective_momentum, is_plain_batchnorm
+
+    class MyBN(nn.BatchNorm2d):
+        pass
+
+    assert is_plain_batchnorm(nn.BatchNorm2d(8))
+    for m in (nn.SyncBatchNorm(8), nn.GroupNorm(2, 8), MyBN(8), nn.Identity(), nn.BatchNorm1d(8)):
+        assert not is_plain_batchnorm(m)
+    bn = nn.BatchNorm2d(8, momentum=0.25)
+    assert effective_momentum(bn) == 0.25
+    bn = nn.BatchNorm2d(8, momentum=None)
+    bn.num_batches_tracked.fill_(3)
+    assert effective_momentum(bn) == pytest.approx(1 / 3)            # counter already incremented by the caller
+    assert effective_momentum(bn, pending=1) == pytest.approx(1 / 4)  # counter incremented after the op
+
+
+def test_flat_gradient_views_keep_parameter_strides():
+    """train.GraphedStep hands every parameter a view of ONE flat fp32 buffer as its .grad; channels_last conv weights keep
+    their strides (so backward kernels write into the buffer without a layout-converting copy)."""
+    import torch
+    from mrla_b200.train import _grad_view
+    flat = torch.zeros(64 * 16 * 3 * 3 + 10)
+    w = torch.randn(64, 16, 3, 3).contiguous(memory_format=torch.channels_last)
+    gv = _grad_view(w, flat[:w.numel()])
+    assert gv.shape == w.shape and gv.stride() == w.stride()
+    gv.copy_(w)
+    assert torch.equal(gv, w) and flat[:w.numel()].abs().sum() > 0        # a view: writes land in the flat buffer
+    b = torch.randn(10)
+    gb = _grad_view(b, flat[w.numel():])
+    assert gb.shape == b.shape and gb.data_ptr() == flat[w.numel():].data_ptr()
+    w2 = torch.randn(8, 4, 1, 1)                                           # dense NCHW weight: plain view
+    assert _grad_view(w2, torch.zeros(32)).stride() == w2.stride()
