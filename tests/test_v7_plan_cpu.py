@@ -104,3 +104,25 @@ def test_fp32_virtual_x_at_eight_column_groups_does_not_fit():
     assert plan(32, 256, 56, 56, 3, True, dtype=_lib.F32)["ok"] == 0
     assert plan(32, 256, 56, 56, 3, True, dtype=_lib.BF16)["ok"] == 1
     assert plan(32, 256, 56, 56, 3, True, dtype=_lib.F16)["ok"] == 1
+
+
+def test_multiply_high_reciprocal_is_exact_in_the_planned_range():
+    """light_v7.cuh::v7_fdiv computes a / d as umulhi(a, ceil(2^32 / d)); v7_plan refuses shapes whose pipeline-row index
+    could leave the range where that is exact (rows * d < 2^32).  Check the arithmetic the kernels rely on, including the
+    largest admitted operands."""
+    import random
+    rnd = random.Random(7)
+
+    def fdiv(a, d):
+        m = ((1 << 32) + d - 1) // d
+        assert m < (1 << 32)
+        return (a * m) >> 32
+
+    for _ in range(20000):
+        d = rnd.randint(2, 1 << rnd.randint(2, 20))
+        amax = ((1 << 32) - 1) // d
+        for a in (0, 1, d - 1, d, d + 1, amax // 2, amax - 1, amax, rnd.randint(0, amax)):
+            if 0 <= a <= amax:
+                assert fdiv(a, d) == a // d, (a, d)
+    # the bound is tight-ish: far outside it the shortcut does go wrong, which is why the planner checks it
+    assert any(fdiv(a, 3) != a // 3 for a in range((1 << 32) - 64, 1 << 32))
